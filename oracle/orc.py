@@ -1,0 +1,292 @@
+"""oracle/orc.py -- ctypes binding of the C restatement (TEST INFRASTRUCTURE ONLY).
+
+PARITY UNPINNED (see tsdr_oracle.h).  Importable only from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+All images cross this boundary in Julia layout (column-major, numpy order="F").
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+if HERE not in sys.path:
+    sys.path.insert(0, HERE)
+import build as _build  # noqa: E402
+
+RENDER_H, RENDER_W = 600, 800
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+class _Sync(C.Structure):
+    _fields_ = [("n_y", C.c_int), ("n_x", C.c_int), ("wmin_y", C.c_int), ("wmax_y", C.c_int),
+                ("wmin_x", C.c_int), ("wmax_x", C.c_int), ("h", C.c_float * 5),
+                ("beta_x", C.POINTER(C.c_float)), ("beta_y", C.POINTER(C.c_float))]
+
+
+def _load():
+    lib = C.CDLL(_build.build())
+    sig = {
+        "orc_hypotf": (C.c_float, [C.c_float, C.c_float]),
+        "orc_am_demod": (None, [_f32p, _f32p, C.c_size_t]),
+        "orc_invert_am_demod": (None, [_f32p, _f32p, C.c_size_t]),
+        "orc_fm_demod": (None, [_f32p, _f32p, C.c_size_t]),
+        "orc_abs2": (None, [_f32p, _f32p, C.c_size_t]),
+        "orc_imresize_1d": (None, [_f32p, C.c_size_t, _f32p, C.c_size_t]),
+        "orc_imresize_2d": (None, [_f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int]),
+        "orc_sig_to_image": (None, [_f32p, C.c_size_t, C.c_int, C.c_int, _f32p]),
+        "orc_downgrade": (None, [_f32p, C.c_int, C.c_int, _f32p]),
+        "orc_naive_resampler": (None, [_f32p, _f32p, C.c_size_t, C.c_int]),
+        "orc_fft_c2c": (C.c_int, [_f32p, _f32p, C.c_size_t, C.c_int]),
+        "orc_autocorr": (C.c_int, [_f32p, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_int,
+                                   _f32p, C.POINTER(C.c_size_t)]),
+        "orc_zoom_window": (None, [C.c_size_t, C.c_double, C.c_double, C.c_double,
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "orc_findmax": (C.c_size_t, [_f32p, C.c_size_t]),
+        "orc_sync_create": (C.POINTER(_Sync), [C.c_int, C.c_int]),
+        "orc_sync_destroy": (None, [C.POINTER(_Sync)]),
+        "orc_proj_cols": (None, [_f32p, C.c_int, C.c_int, _f32p]),
+        "orc_proj_rows": (None, [_f32p, C.c_int, C.c_int, _f32p]),
+        "orc_filt5": (None, [_f32p, _f32p, _f32p, C.c_int]),
+        "orc_fill_beta": (None, [_f32p, _f32p, C.c_int, C.c_int, C.c_int]),
+        "orc_argmax_col": (C.c_int, [_f32p, C.c_int, C.c_int]),
+        "orc_vsync": (None, [C.POINTER(_Sync), _f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "orc_circshift": (None, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "orc_ema": (None, [_f32p, _f32p, C.c_size_t, C.c_float]),
+        "orc_full_scale": (None, [_f32p, _f32p, C.c_size_t]),
+        "orc_round_even": (C.c_int64, [C.c_double]),
+        "orc_frame_samples": (C.c_int64, [C.c_double, C.c_double]),
+        "orc_chain_buffer": (C.c_int, [_f32p, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_double, C.c_float,
+                                       C.POINTER(_Sync), _f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+        "orc_num_threads": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+lib = _load()
+
+
+def _iq(x):
+    """complex64 vector -> interleaved float32 view (ComplexF32 memory layout)."""
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    return x.view(np.float32), x.size
+
+
+def _cm(img):
+    """2-D array -> flat float32 buffer in column-major (Julia) order."""
+    return np.ascontiguousarray(np.asarray(img, dtype=np.float32).T).ravel()
+
+
+def _from_cm(flat, h, w):
+    return flat.reshape(w, h).T  # element (r, c) at r + h*c
+
+
+def hypot(x, y):
+    return np.float32(lib.orc_hypotf(np.float32(x), np.float32(y)))
+
+
+def amDemod(sig):  # src/Demodulation.jl:26-28
+    v, n = _iq(sig)
+    out = np.empty(n, np.float32)
+    lib.orc_am_demod(v, out, n)
+    return out
+
+
+def invert_amDemod(sig):  # src/Demodulation.jl:31-35
+    v, n = _iq(sig)
+    out = np.empty(n, np.float32)
+    lib.orc_invert_am_demod(v, out, n)
+    return out
+
+
+def fmDemod(sig):  # src/Demodulation.jl:17-23
+    v, n = _iq(sig)
+    out = np.empty(n, np.float32)
+    lib.orc_fm_demod(v, out, n)
+    return out
+
+
+def abs2(sig):  # src/GUI.jl:70
+    v, n = _iq(sig)
+    out = np.empty(n, np.float32)
+    lib.orc_abs2(v, out, n)
+    return out
+
+
+def imresize_1d(sig, n_out):
+    sig = np.ascontiguousarray(sig, np.float32)
+    out = np.empty(n_out, np.float32)
+    lib.orc_imresize_1d(sig, sig.size, out, n_out)
+    return out
+
+
+def imresize_2d(img, h_out, w_out):
+    h, w = img.shape
+    out = np.empty(h_out * w_out, np.float32)
+    lib.orc_imresize_2d(_cm(img), h, w, out, h_out, w_out)
+    return _from_cm(out, h_out, w_out)
+
+
+def sig_to_image(sig, y_t, x_t):  # src/Resampler.jl:117-122 -> (y_t, x_t) array
+    sig = np.ascontiguousarray(sig, np.float32)
+    out = np.empty(y_t * x_t, np.float32)
+    lib.orc_sig_to_image(sig, sig.size, y_t, x_t, out)
+    return _from_cm(out, y_t, x_t)
+
+
+def downgradeImage(img):  # src/Resampler.jl:124-126
+    return imresize_2d(img, RENDER_H, RENDER_W)
+
+
+def naiveResampler(sig, up):  # src/Resampler.jl:103-110
+    sig = np.ascontiguousarray(sig, np.float32)
+    out = np.empty(sig.size * up, np.float32)
+    lib.orc_naive_resampler(out, sig, sig.size, up)
+    return out
+
+
+def fft(x, inverse=False):
+    v, n = _iq(x)
+    out = np.empty(2 * n, np.float32)
+    if lib.orc_fft_c2c(v, out, n, int(inverse)):
+        raise MemoryError
+    return out.view(np.complex64)
+
+
+def calculate_autocorrelation(x, Fs, minDelay, maxDelay, scale="log"):  # src/Autocorrelations.jl:23-37
+    x = np.ascontiguousarray(x, np.float32)
+    imin = 1 + int(lib.orc_round_even(minDelay * Fs))
+    imax = int(lib.orc_round_even(maxDelay * Fs))
+    out = np.empty(max(imax - imin + 1, 1), np.float32)
+    n_out = C.c_size_t(0)
+    rc = lib.orc_autocorr(x, x.size, Fs, minDelay, maxDelay, int(scale == "log"), out, C.byref(n_out))
+    if rc == -1:
+        raise IndexError("BoundsError: signal shorter than indexMax")
+    if rc:
+        raise ValueError("orc_autocorr rc=%d" % rc)
+    lags = np.arange(0, imax - imin + 1, dtype=np.float64) * 1 / Fs
+    return out[: n_out.value], lags
+
+
+def zoom_autocorr(gamma, Fs, rate_min=20, rate_max=100):  # src/Autocorrelations.jl:42-53
+    a, b = C.c_int64(0), C.c_int64(0)
+    lib.orc_zoom_window(len(gamma), Fs, float(rate_min), float(rate_max), C.byref(a), C.byref(b))
+    idx = np.arange(a.value, b.value + 1, dtype=np.float64)
+    rates = 1.0 / (idx / Fs)
+    return rates, np.asarray(gamma)[a.value - 1: b.value]
+
+
+def findmax(v):
+    v = np.ascontiguousarray(v, np.float32)
+    i = lib.orc_findmax(v, v.size)
+    return v[i], i + 1  # 1-based like Julia
+
+
+class SyncXY:  # src/FrameSynchronisation.jl:25-48
+    def __init__(self, n_y=RENDER_H, n_x=RENDER_W):
+        self._p = lib.orc_sync_create(n_y, n_x)
+        s = self._p.contents
+        self.n_y, self.n_x = s.n_y, s.n_x
+        self.wmin_y, self.wmax_y, self.wmin_x, self.wmax_x = s.wmin_y, s.wmax_y, s.wmin_x, s.wmax_x
+        self.h = np.array(list(s.h), np.float32)
+
+    def beta_x(self):
+        nw = 1 + self.wmax_x - self.wmin_x
+        return np.ctypeslib.as_array(self._p.contents.beta_x, (self.n_x, nw)).T.copy()  # (nw, n_x)
+
+    def beta_y(self):
+        nw = 1 + self.wmax_y - self.wmin_y
+        return np.ctypeslib.as_array(self._p.contents.beta_y, (self.n_y, nw)).T.copy()
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib.orc_sync_destroy(self._p)
+            self._p = None
+
+
+def vsync(img, sync):  # src/FrameSynchronisation.jl:56-79 -> (s_y, s_x), 1-based
+    sy, sx = C.c_int(0), C.c_int(0)
+    lib.orc_vsync(sync._p, _cm(img), C.byref(sy), C.byref(sx))
+    return sy.value, sx.value
+
+
+def proj_cols(img):
+    h, w = img.shape
+    out = np.empty(w, np.float32)
+    lib.orc_proj_cols(_cm(img), h, w, out)
+    return out
+
+
+def proj_rows(img):
+    h, w = img.shape
+    out = np.empty(h, np.float32)
+    lib.orc_proj_rows(_cm(img), h, w, out)
+    return out
+
+
+def filt5(h, x):
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.empty_like(x)
+    lib.orc_filt5(np.ascontiguousarray(h, np.float32), x, y, x.size)
+    return y
+
+
+def fill_beta(c, wmin, wmax):
+    c = np.ascontiguousarray(c, np.float32)
+    nw = 1 + wmax - wmin
+    beta = np.empty(nw * c.size, np.float32)
+    lib.orc_fill_beta(beta, c, c.size, wmin, wmax)
+    return beta.reshape(c.size, nw).T  # (nw, n): Julia's beta[cnt, c]
+
+
+def circshift(img, s_y, s_x):  # src/GUI.jl:172 : circshift(img, (-s_y, -s_x))
+    h, w = img.shape
+    out = np.empty(h * w, np.float32)
+    lib.orc_circshift(_cm(img), out, h, w, s_y, s_x)
+    return _from_cm(out, h, w)
+
+
+def ema(acc, img, alpha):  # src/GUI.jl:175, returns the new accumulator
+    a = np.ascontiguousarray(acc, np.float32).ravel().copy()
+    lib.orc_ema(a, np.ascontiguousarray(img, np.float32).ravel(), a.size, np.float32(alpha))
+    return a.reshape(np.shape(acc))
+
+
+def fullScale(mat):  # src/ScreenRenderer.jl:35-39
+    m = np.ascontiguousarray(mat, np.float32)
+    out = np.empty_like(m)
+    lib.orc_full_scale(m.ravel(), out.ravel(), m.size)
+    return out
+
+
+def frame_samples(Fs, fv):  # src/GUI.jl:103-109
+    return int(lib.orc_frame_samples(Fs, fv))
+
+
+def chain_buffer(iq, Fs, x_t, y_t, fv, alpha, sync, image_out, publish=True, nthreads=1):
+    """coreProcessing loop body for one buffer (src/GUI.jl:163-178).
+    image_out: (600, 800) float32 EMA state; returns (new image_out, frames or None, sy, sx)."""
+    v, n = _iq(iq)
+    S = frame_samples(Fs, fv)
+    nb = n // S
+    acc = _cm(image_out).copy()
+    frames = np.empty(nb * RENDER_H * RENDER_W, np.float32) if publish else None
+    sy = np.zeros(max(nb, 1), np.int32)
+    sx = np.zeros(max(nb, 1), np.int32)
+    got = lib.orc_chain_buffer(v, n, Fs, x_t, y_t, fv, np.float32(alpha), sync._p, acc,
+                               frames.ctypes.data if publish else None,
+                               sy.ctypes.data, sx.ctypes.data, nthreads)
+    assert got == nb
+    fr = None
+    if publish:
+        fr = frames.reshape(nb, RENDER_W, RENDER_H).transpose(0, 2, 1)
+    return _from_cm(acc, RENDER_H, RENDER_W), fr, sy[:nb], sx[:nb]
+
+
+def num_threads():
+    return lib.orc_num_threads()

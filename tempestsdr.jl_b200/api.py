@@ -1,0 +1,363 @@
+"""Host-side mirror of the reference's exported DSP functions (src/TempestSDR.jl:21-47).
+
+Same names, argument meaning and error behaviour as the Julia functions; every
+compute call goes through the C ABI of libtempest_b200.so (hand-written sm_100a
+CUDA).  There is no CPU implementation in this module: without the library or
+without a GPU the calls raise.  Matrices are numpy arrays indexed [row, col] and
+cross the ABI in Julia's column-major layout.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import TempestError, check
+from .video_configurations import (VideoMode, allVideoConfigurations, find_closest_configuration,  # noqa: F401
+                                   find_configuration, get_refresh_rates, dict2video)
+
+__all__ = [
+    "amDemod", "invert_amDemod", "fmDemod", "abs2", "sig_to_image", "downgradeImage", "naiveResampler",
+    "calculate_autocorrelation", "zoom_autocorr", "findmax", "SyncXY", "vsync", "fullScale",
+    "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
+    "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
+    "Chain", "AutocorrPlan", "extract_configuration", "estimate_lines", "TempestError", "RENDERING_SIZE",
+    "device_count",
+]
+
+RENDERING_SIZE = (600, 800)  # src/GUI.jl:10
+
+
+def device_count():
+    return _lib.device_count()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _iq(sig):
+    z = np.ascontiguousarray(sig, dtype=np.complex64)
+    return z, z.size
+
+
+def _demod(fn, sig):
+    z, n = _iq(sig)
+    out = np.empty(n, np.float32)
+    check(fn(_ptr(z), _ptr(out), n))
+    return out
+
+
+def amDemod(sig):
+    """abs.(sig) -- src/Demodulation.jl:26-28"""
+    return _demod(_lib.load().tsdr_am_demod_f32, sig)
+
+
+def invert_amDemod(sig):
+    """1 .- abs.(sig) ./ maximum(abs.(sig)) -- src/Demodulation.jl:31-35"""
+    return _demod(_lib.load().tsdr_invert_am_demod_f32, sig)
+
+
+def fmDemod(sig):
+    """angle(sig[n+1] * conj(sig[n])) -- src/Demodulation.jl:17-23"""
+    return _demod(_lib.load().tsdr_fm_demod_f32, sig)
+
+
+def abs2(sig):
+    """abs2.(sig), what extract_configuration feeds the autocorrelation -- src/GUI.jl:70"""
+    return _demod(_lib.load().tsdr_abs2_f32, sig)
+
+
+def sig_to_image(sig, y_t, x_t):
+    """imresize(sig, y_t*x_t) |> reshape(x_t, y_t) |> transpose -- src/Resampler.jl:117-122
+    Returns a (y_t, x_t) matrix whose row r is scan line r."""
+    s = np.ascontiguousarray(sig, dtype=np.float32)
+    out = np.empty((int(y_t), int(x_t)), np.float32, order="F")
+    check(_lib.load().tsdr_sig_to_image_f32(_ptr(s), s.size, int(y_t), int(x_t), _ptr(out)))
+    return out
+
+
+def downgradeImage(image):
+    """imresize(image, (600, 800)) -- src/Resampler.jl:124-126"""
+    img = np.asfortranarray(image, dtype=np.float32)
+    out = np.empty(RENDERING_SIZE, np.float32, order="F")
+    check(_lib.load().tsdr_downgrade_f32(_ptr(img), img.shape[0], img.shape[1], _ptr(out)))
+    return out
+
+
+def naiveResampler(sigOut, sigId, upCoeff):
+    """sample-and-hold upsampler writing into sigOut -- src/Resampler.jl:103-110"""
+    s = np.ascontiguousarray(sigId, dtype=np.float32)
+    if not (isinstance(sigOut, np.ndarray) and sigOut.dtype == np.float32 and sigOut.flags.c_contiguous):
+        raise TypeError("sigOut must be a contiguous float32 array")
+    if sigOut.size < s.size * int(upCoeff):
+        raise IndexError("BoundsError: sigOut shorter than upCoeff*length(sigId)")
+    check(_lib.load().tsdr_naive_resampler_f32(_ptr(sigOut), _ptr(s), s.size, int(upCoeff)))
+    return None
+
+
+def _round(x):  # Base.round, ties to even
+    return int(np.rint(np.float64(x)))
+
+
+def calculate_autocorrelation(x, Fs, minDelay, maxDelay, scale="log"):
+    """(Gamma, lags) -- src/Autocorrelations.jl:23-37.  scale: "log" (:log) or anything else (abs2)."""
+    xs = np.ascontiguousarray(x, dtype=np.float32)
+    n_out = C.c_size_t(0)
+    lib = _lib.load()
+    rc = lib.tsdr_autocorr_out_len(xs.size, float(Fs), float(minDelay), float(maxDelay), C.byref(n_out))
+    if rc == -5:
+        raise IndexError("BoundsError: " + lib.tsdr_last_error_string().decode())
+    check(rc)
+    out = np.empty(n_out.value, np.float32)
+    check(lib.tsdr_autocorr_f32(_ptr(xs), xs.size, float(Fs), float(minDelay), float(maxDelay),
+                                1 if scale in ("log", ":log") else 0, _ptr(out), C.byref(n_out)))
+    nbS = _round(maxDelay * Fs) - (1 + _round(minDelay * Fs))
+    lags = np.arange(0, nbS + 1, dtype=np.float64) * 1 / Fs
+    return out, lags
+
+
+def zoom_autocorr(Gamma, Fs, rate_min=20, rate_max=100):
+    """(rates, Gamma[pos_rate_min:pos_rate_max]) -- src/Autocorrelations.jl:42-53 (host-side slicing).
+    Keeps the reference's convention that index k stands for lag k/Fs."""
+    N = len(Gamma)
+    pos_rate_min = min(_round(1 / rate_max * Fs), N)
+    pos_rate_max = min(_round(1 / rate_min * Fs), N)
+    xAx = np.arange(pos_rate_min, pos_rate_max + 1, dtype=np.float64) / Fs
+    return 1.0 / xAx, np.asarray(Gamma)[pos_rate_min - 1: pos_rate_max]
+
+
+def findmax(v):
+    """(value, 1-based index) of the first maximum, NaN dominating (Base.findmax), on the GPU."""
+    a = np.ascontiguousarray(v, dtype=np.float32)
+    val, idx = C.c_float(0), C.c_size_t(0)
+    check(_lib.load().tsdr_findmax_f32(_ptr(a), a.size, C.byref(val), C.byref(idx)))
+    return np.float32(val.value), idx.value
+
+
+def fullScale(mat):
+    """(mat .- min) / (max - min) -- src/ScreenRenderer.jl:35-39"""
+    m = np.ascontiguousarray(mat, dtype=np.float32)
+    out = np.empty_like(m)
+    check(_lib.load().tsdr_full_scale_f32(_ptr(m), _ptr(out), m.size))
+    return out
+
+
+class SyncXY:
+    """SyncXY(image) -- src/FrameSynchronisation.jl:25-48.  Owns beta_x / beta_y on the device."""
+
+    def __init__(self, image=None):
+        shape = RENDERING_SIZE if image is None else np.shape(image)
+        h = C.c_void_p()
+        check(_lib.load().tsdr_sync_create(int(shape[0]), int(shape[1]), C.byref(h)))
+        self._h = h
+        self.n_y, self.n_x = int(shape[0]), int(shape[1])
+        b = [C.c_int(0) for _ in range(4)]
+        check(_lib.load().tsdr_sync_bounds(self._h, *[C.byref(v) for v in b]))
+        self.wmin_y, self.wmax_y, self.wmin_x, self.wmax_x = [v.value for v in b]
+
+    def _betas(self):
+        bx = np.empty((1 + self.wmax_x - self.wmin_x, self.n_x), np.float32, order="F")
+        by = np.empty((1 + self.wmax_y - self.wmin_y, self.n_y), np.float32, order="F")
+        check(_lib.load().tsdr_sync_get_beta(self._h, _ptr(bx), _ptr(by)))
+        return bx, by
+
+    @property
+    def beta_x(self):
+        return self._betas()[0]
+
+    @property
+    def beta_y(self):
+        return self._betas()[1]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().tsdr_sync_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def vsync(image, sync):
+    """(s_y, s_x), 1-based -- src/FrameSynchronisation.jl:56-79 (s_y comes from the previous call's beta_y)."""
+    img = np.asfortranarray(image, dtype=np.float32)
+    if img.shape != (sync.n_y, sync.n_x):
+        raise ValueError("image shape %s does not match SyncXY %s" % (img.shape, (sync.n_y, sync.n_x)))
+    sy, sx = C.c_int(0), C.c_int(0)
+    check(_lib.load().tsdr_vsync_f32(sync._h, _ptr(img), C.byref(sy), C.byref(sx)))
+    return sy.value, sx.value
+
+
+def getImageDuration(theConfig, Fs):
+    """round(Fs / refresh) -- src/GUI.jl:103-109"""
+    return _round(Fs / theConfig.refresh)
+
+
+def delay2yt(tau_or_index, *args):  # src/GUI.jl:238-243
+    if len(args) == 1:
+        return float(np.rint(1 / (args[0] * tau_or_index)))
+    Fs, fv = args
+    return float(np.rint(1 / (fv * (tau_or_index / Fs))))
+
+
+def yt2index(yt, Fs, fv):  # src/GUI.jl:247-249
+    return float(np.rint(Fs / (fv * yt)))
+
+
+def yt2delay(yt, fv):  # src/GUI.jl:250-252
+    return 1 / (fv * yt)
+
+
+class Chain:
+    """The loop body of coreProcessing (src/GUI.jl:163-178) as one device-resident object:
+    amDemod -> sig_to_image -> downgradeImage -> vsync -> circshift -> EMA for every
+    frame of a recv! buffer.
+
+        ch = Chain(Fs, VideoMode(2576, 1125, 60), alpha=0.1, max_samples=10_000_000)
+        n_frames = ch.push(iq)            # numpy complex64 (host) ...
+        n_frames = ch.push_device(ptr, n) # ... or a device pointer to interleaved float32
+        img = ch.image()                  # imageOut, (600, 800)
+    """
+
+    def __init__(self, Fs, config, alpha=0.1, max_samples=None, device=0, publish_all=False, do_align=True,
+                 sum_mode=False, stream=None):
+        if max_samples is None:
+            max_samples = getImageDuration(config, Fs)
+        flags = (_lib.TSDR_CHAIN_PUBLISH_ALL if publish_all else 0) | (0 if do_align else _lib.TSDR_CHAIN_NO_ALIGN) \
+            | (_lib.TSDR_CHAIN_SUM if sum_mode else 0)
+        h = C.c_void_p()
+        check(_lib.load().tsdr_chain_create(C.byref(h), int(device), float(Fs), int(config.width), int(config.height),
+                                            float(config.refresh), float(alpha), int(max_samples), flags,
+                                            C.c_void_p(stream) if stream else None))
+        self._h = h
+        self.Fs, self.config, self.device = float(Fs), config, int(device)
+        self.S = getImageDuration(config, Fs)
+        self.max_samples = int(max_samples)
+        self.publish_all = publish_all
+
+    def configure(self, Fs, config):  # FLAG_CONFIG_UPDATE, src/GUI.jl:151-158
+        check(_lib.load().tsdr_chain_configure(self._h, float(Fs), int(config.width), int(config.height),
+                                               float(config.refresh)))
+        self.Fs, self.config, self.S = float(Fs), config, getImageDuration(config, Fs)
+
+    def set_alpha(self, alpha):  # OBS_alpha, src/GUI.jl:160
+        check(_lib.load().tsdr_chain_set_alpha(self._h, float(alpha)))
+
+    def reset(self):
+        check(_lib.load().tsdr_chain_reset(self._h))
+
+    def push(self, iq):
+        """one recv! buffer from host memory (numpy complex64, or a pinned torch tensor's numpy view)"""
+        z, n = _iq(iq)
+        nf = C.c_int(0)
+        check(_lib.load().tsdr_chain_push_host(self._h, _ptr(z), n, C.byref(nf)))
+        self._keep = z  # the copy is asynchronous: keep the buffer alive until the next sync
+        return nf.value
+
+    def push_host_ptr(self, ptr, n):
+        nf = C.c_int(0)
+        check(_lib.load().tsdr_chain_push_host(self._h, C.c_void_p(ptr), int(n), C.byref(nf)))
+        return nf.value
+
+    def push_device(self, ptr, n):
+        nf = C.c_int(0)
+        check(_lib.load().tsdr_chain_push_device(self._h, C.c_void_p(ptr), int(n), C.byref(nf)))
+        return nf.value
+
+    def sync(self):
+        check(_lib.load().tsdr_chain_sync(self._h))
+
+    def image(self):
+        out = np.empty(RENDERING_SIZE, np.float32, order="F")
+        check(_lib.load().tsdr_chain_read_image(self._h, _ptr(out)))
+        return out
+
+    def offsets(self, max_frames=65536):
+        sy = np.zeros(max_frames, np.int32)
+        sx = np.zeros(max_frames, np.int32)
+        n = C.c_int(0)
+        check(_lib.load().tsdr_chain_read_offsets(self._h, _ptr(sy), _ptr(sx), max_frames, C.byref(n)))
+        k = min(n.value, max_frames)
+        return sy[:k].copy(), sx[:k].copy()
+
+    def published(self, max_frames=None):
+        """every intermediate imageOut of the last buffer (non_blocking_put!, src/GUI.jl:177)"""
+        if max_frames is None:
+            max_frames = self.max_samples // self.S
+        buf = np.empty((max_frames, RENDERING_SIZE[1], RENDERING_SIZE[0]), np.float32)
+        n = C.c_int(0)
+        check(_lib.load().tsdr_chain_read_published(self._h, _ptr(buf), max_frames, C.byref(n)))
+        k = min(n.value, max_frames)
+        return buf[:k].transpose(0, 2, 1)  # each frame column-major -> [row, col] view
+
+    def accumulator_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t(0)
+        check(_lib.load().tsdr_chain_accumulator(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def scale_accumulator(self, factor):
+        check(_lib.load().tsdr_chain_scale_accumulator(self._h, float(factor)))
+
+    def stream(self):
+        p = C.c_void_p()
+        check(_lib.load().tsdr_chain_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def launch_count(self):
+        v = C.c_uint64(0)
+        check(_lib.load().tsdr_chain_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().tsdr_chain_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class AutocorrPlan:
+    """Device-resident calculate_autocorrelation for a fixed length n (the measured M2 path)."""
+
+    def __init__(self, n, device=0, stream=None):
+        h = C.c_void_p()
+        check(_lib.load().tsdr_autocorr_plan_create(C.byref(h), int(device), int(n),
+                                                    C.c_void_p(stream) if stream else None))
+        self._h, self.n = h, int(n)
+
+    def exec(self, x_dev_ptr, index_min, index_max, out_dev_ptr, log_scale=True):
+        check(_lib.load().tsdr_autocorr_plan_exec(self._h, C.c_void_p(x_dev_ptr), int(index_min), int(index_max),
+                                                  1 if log_scale else 0, C.c_void_p(out_dev_ptr)))
+
+    def launch_count(self):
+        v = C.c_uint64(0)
+        check(_lib.load().tsdr_autocorr_plan_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().tsdr_autocorr_plan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def extract_configuration(sig_corr, Fs, delayRate=1 / 10, rate_min=50, rate_max=90):
+    """Numerical part of extract_configuration (src/GUI.jl:49-88): sig_corr is the
+    abs2 power signal the reference assembles from nbBuffer recv! calls (:67-71).
+    Returns (rates_refresh, Gamma_refresh, fv)."""
+    Gamma, _ = calculate_autocorrelation(sig_corr, Fs, 0, delayRate)
+    rates_refresh, Gamma_refresh = zoom_autocorr(Gamma, Fs, rate_min=rate_min, rate_max=rate_max)
+    _, posMax = findmax(Gamma_refresh)
+    posMax_time = 1 / rates_refresh[posMax - 1]
+    fv = 1 / posMax_time
+    return rates_refresh, Gamma_refresh, fv
+
+
+def estimate_lines(Gamma, Fs, fv, N=500):
+    """Headless line-count pick of production/investigate_data.jl:69-82:
+    zoom to [fv, fv+0.3] Hz, first N lags, findmax -> y_t = 1/(fv * m/Fs)."""
+    _, Gamma_short = zoom_autocorr(Gamma, Fs, rate_min=fv, rate_max=fv + 0.3)
+    Gamma_short = Gamma_short[:N]
+    m = findmax(Gamma_short)[1]
+    tau = m / Fs
+    return 1 / (fv * tau)

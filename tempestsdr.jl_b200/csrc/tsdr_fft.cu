@@ -1,0 +1,563 @@
+// tsdr_fft.cu -- hand-written FFT autocorrelation for sm_100a (no cuFFT, no tensor cores).
+//
+// Replaces calculate_autocorrelation (src/Autocorrelations.jl:23-37):
+//     theCorr = ifft(fft(x) .* conj(fft(x)));  10*log10.(abs2.(theCorr[indexMin:indexMax]))
+//
+// Design (DESIGN.md "K5"): the input is real, so the N-point transforms run as
+// M = N/2 point complex transforms of z[j] = x[2j] + i x[2j+1].  M = A*B is split
+// four-step style and the whole autocorrelation takes THREE kernels:
+//   k_fft_cols   A-point forward FFTs down the columns (stride B) + twiddle W_M^(j2 k1)
+//   k_fft_mid    per pair of rows (k1, A-k1): B-point forward FFT, real-input unpack,
+//                |X|^2, Hermitian repack, B-point inverse FFT, twiddle -- all in shared memory
+//   k_ifft_cols  A-point inverse FFTs down the columns, epilogue 10*log10(r^2) of the lag slice
+// Every in-shared-memory FFT is an in-place radix-16/8/4/2 register butterfly network
+// (decimation in frequency forward, decimation in time inverse), so no bit-reversal pass
+// is ever needed: the forward result stays in digit-reversed order and the matching
+// inverse consumes it.  Global traffic: 5 * 8M + 4L bytes.
+// Lengths that are not a power of two use the zero-padded transform of size
+// N >= 2n and fold the linear lags: r_circ[k] = r_lin[k] + r_lin[n-k].
+#include "tsdr_internal.cuh"
+
+#include <new>
+#include <vector>
+
+namespace tsdr {
+
+// ---------------------------------------------------------------- helpers --
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// multiply by -i (DIR=+1, forward) or +i (DIR=-1, inverse)
+template <int DIR> __device__ __forceinline__ float2 mul_mi(float2 a) {
+    return DIR > 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+template <int DIR> __device__ __forceinline__ float2 mul_c(float2 a, float c, float s) {  // a * (c - i s) fwd, (c + i s) inv
+    const float ss = DIR > 0 ? -s : s;
+    return make_float2(fmaf(a.x, c, -a.y * ss), fmaf(a.x, ss, a.y * c));
+}
+
+// R-point DFT in registers, natural order in and out.  DIR=+1: e^{-2 pi i pq/R}.
+template <int DIR> __device__ __forceinline__ void dft2(float2& a, float2& b) {
+    const float2 t = csub(a, b); a = cadd(a, b); b = t;
+}
+template <int DIR> __device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = mul_mi<DIR>(csub(x1, x3));
+    x0 = cadd(t0, t2); x2 = csub(t0, t2); x1 = cadd(t1, t3); x3 = csub(t1, t3);
+}
+template <int DIR> __device__ __forceinline__ void dft8(float2* x) {  // x[0..7]
+    float2 e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6], o0 = x[1], o1 = x[3], o2 = x[5], o3 = x[7];
+    dft4<DIR>(e0, e1, e2, e3);
+    dft4<DIR>(o0, o1, o2, o3);
+    const float h = 0.70710678118654752440f;
+    o1 = mul_c<DIR>(o1, h, h);
+    o2 = mul_mi<DIR>(o2);
+    o3 = mul_c<DIR>(o3, -h, h);
+    x[0] = cadd(e0, o0); x[4] = csub(e0, o0);
+    x[1] = cadd(e1, o1); x[5] = csub(e1, o1);
+    x[2] = cadd(e2, o2); x[6] = csub(e2, o2);
+    x[3] = cadd(e3, o3); x[7] = csub(e3, o3);
+}
+template <int DIR> __device__ __forceinline__ void dft16(float2* x) {
+    float2 e[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { e[i] = x[2 * i]; o[i] = x[2 * i + 1]; }
+    dft8<DIR>(e);
+    dft8<DIR>(o);
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    o[1] = mul_c<DIR>(o[1], c1, s1);
+    o[2] = mul_c<DIR>(o[2], h, h);
+    o[3] = mul_c<DIR>(o[3], s1, c1);
+    o[4] = mul_mi<DIR>(o[4]);
+    o[5] = mul_c<DIR>(o[5], -s1, c1);
+    o[6] = mul_c<DIR>(o[6], -h, h);
+    o[7] = mul_c<DIR>(o[7], -c1, s1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = cadd(e[i], o[i]); x[i + 8] = csub(e[i], o[i]); }
+}
+template <int R, int DIR> __device__ __forceinline__ void dft(float2* x) {
+    if (R == 2) dft2<DIR>(x[0], x[1]);
+    else if (R == 4) dft4<DIR>(x[0], x[1], x[2], x[3]);
+    else if (R == 8) dft8<DIR>(x);
+    else dft16<DIR>(x);
+}
+
+// shared-memory layouts (element = float2).  Rows: contiguous transform, one pad
+// element per 16.  Cols: C interleaved transforms (element (i, col) at i*C + col),
+// 8 pad elements per 128 so that radix blocks land in different banks.
+struct RowLayout {
+    int row_stride;
+    __device__ __forceinline__ int operator()(int b, int i) const { return b * row_stride + i + (i >> 4); }
+};
+struct ColLayout {
+    int C;
+    __device__ __forceinline__ int operator()(int b, int i) const { const int e = i * C + b; return e + ((e >> 7) << 3); }
+};
+__host__ __device__ inline int row_padded(int len) { return len + (len >> 4) + 1; }
+__host__ __device__ inline int col_padded(int total) { return total + ((total >> 7) << 3) + 8; }
+
+// One in-place stage on sub-transforms of length Lcur (radix R, butterfly stride Lcur/R).
+//  FWD (DIF): y = DFT_R(x); y[p] *= W_Lcur^(u p)
+//  INV (DIT): x[q] *= conj W_Lcur^(u q); y = IDFT_R(x)
+// tw = table of W_len^k, k in [0, len).  COLFAST: batch index varies fastest over threads.
+template <int R, int DIR, bool COLFAST, class Layout>
+__device__ __forceinline__ void fft_stage(float2* s, const Layout lay, int nbatch, int len, int Lcur,
+                                          const float2* __restrict__ tw, int tid, int nthr) {
+    const int sub = Lcur / R;
+    const int per = len / R;
+    const int tws = len / Lcur;
+    for (int e = tid; e < nbatch * per; e += nthr) {
+        int b, w;
+        if (COLFAST) { b = e % nbatch; w = e / nbatch; } else { b = e / per; w = e - b * per; }
+        const int blk = w / sub, u = w - blk * sub;
+        const int base = blk * Lcur + u;
+        float2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = s[lay(b, base + q * sub)];
+        if (DIR < 0 && u != 0) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], cconj(__ldg(tw + u * q * tws)));
+        }
+        dft<R, DIR>(x);
+        if (DIR > 0 && u != 0) {
+#pragma unroll
+            for (int p = 1; p < R; ++p) x[p] = cmul(x[p], __ldg(tw + u * p * tws));
+        }
+#pragma unroll
+        for (int p = 0; p < R; ++p) s[lay(b, base + p * sub)] = x[p];
+    }
+}
+
+struct Radices { int n; int r[8]; };
+
+template <int DIR, bool COLFAST, class Layout>
+__device__ __forceinline__ void fft_inplace(float2* s, const Layout lay, int nbatch, int len, const Radices rad,
+                                            const float2* __restrict__ tw, int tid, int nthr) {
+    if (DIR > 0) {
+        int Lcur = len;
+        for (int i = 0; i < rad.n; ++i) {
+            const int R = rad.r[i];
+            if (R == 16) fft_stage<16, DIR, COLFAST>(s, lay, nbatch, len, Lcur, tw, tid, nthr);
+            else if (R == 8) fft_stage<8, DIR, COLFAST>(s, lay, nbatch, len, Lcur, tw, tid, nthr);
+            else if (R == 4) fft_stage<4, DIR, COLFAST>(s, lay, nbatch, len, Lcur, tw, tid, nthr);
+            else fft_stage<2, DIR, COLFAST>(s, lay, nbatch, len, Lcur, tw, tid, nthr);
+            Lcur /= R;
+            __syncthreads();
+        }
+    } else {
+        int Lcur = 1;
+        for (int i = rad.n - 1; i >= 0; --i) {
+            const int R = rad.r[i];
+            Lcur *= R;
+            if (R == 16) fft_stage<16, DIR, COLFAST>(s, lay, nbatch, len, Lcur, tw, tid, nthr);
+            else if (R == 8) fft_stage<8, DIR, COLFAST>(s, lay, nbatch, len, Lcur, tw, tid, nthr);
+            else if (R == 4) fft_stage<4, DIR, COLFAST>(s, lay, nbatch, len, Lcur, tw, tid, nthr);
+            else fft_stage<2, DIR, COLFAST>(s, lay, nbatch, len, Lcur, tw, tid, nthr);
+            __syncthreads();
+        }
+    }
+}
+
+struct FftParams {
+    int A, B, C;           // M = A*B, C columns per CTA in the column passes
+    int64_t M;
+    Radices radA, radB;
+    const float2* twA;     // W_A^k
+    const float2* twB;     // W_B^k
+    const int* revA;       // row position -> k1
+    const int* posA;       // k1 -> row position
+    const int* revB;       // position -> k2
+    const int* posB;       // k2 -> position
+    const float2* wlo;     // W_N^t,        t in [0, LO)
+    const float2* whi;     // W_N^(t*LO),   t in [0, N/LO)
+    int lo_bits;
+    const float* x;        // real input, n valid samples (zero beyond)
+    int64_t n_valid;
+    float2* T;             // workspace M complex
+    float2* U;             // workspace M complex
+    float inv_scale;       // 1/M
+    // epilogue
+    float* out;            // lag slice, or raw linear lags when fold != 0
+    int64_t m_lo, m_hi;    // 0-based lag range to write
+    int log_scale;
+    int raw;               // write r (not r^2 / dB): used by the fold path
+};
+
+__device__ __forceinline__ float2 twiddle_n(const FftParams& p, int64_t t) {  // W_N^t, 0 <= t < N
+    const float2 lo = __ldg(p.wlo + (t & ((1 << p.lo_bits) - 1)));
+    const float2 hi = __ldg(p.whi + (t >> p.lo_bits));
+    return cmul(lo, hi);
+}
+
+constexpr int kFftThreads = 512;
+
+// ------------------------------------------------------------ k_fft_cols --
+// z[j1*B + j2] (the real input reinterpreted as complex pairs) -> A-point forward FFT
+// over j1 for C adjacent columns j2 -> * W_M^(j2 k1) -> T[row][j2], row = digit-reversed k1.
+__global__ void __launch_bounds__(kFftThreads) k_fft_cols(FftParams p) {
+    extern __shared__ float2 sm[];
+    const int tid = threadIdx.x;
+    const int j2_0 = blockIdx.x * p.C;
+    const ColLayout lay{p.C};
+    const int total = p.A * p.C;
+    // load: consecutive threads read consecutive columns of one row (C*8 contiguous bytes)
+    for (int e = tid; e < total; e += kFftThreads) {
+        const int j1 = e / p.C, col = e - j1 * p.C;
+        const int64_t j = (int64_t)j1 * p.B + j2_0 + col;
+        float2 v;
+        if (2 * j + 1 < p.n_valid) v = __ldg(reinterpret_cast<const float2*>(p.x) + j);
+        else { v.x = (2 * j < p.n_valid) ? __ldg(p.x + 2 * j) : 0.f; v.y = 0.f; }
+        sm[lay(col, j1)] = v;
+    }
+    __syncthreads();
+    fft_inplace<+1, true>(sm, lay, p.C, p.A, p.radA, p.twA, tid, kFftThreads);
+    for (int e = tid; e < total; e += kFftThreads) {
+        const int row = e / p.C, col = e - row * p.C;
+        const int k1 = __ldg(p.revA + row);
+        const int j2 = j2_0 + col;
+        float2 v = sm[lay(col, row)];
+        v = cmul(v, twiddle_n(p, 2 * (int64_t)j2 * k1));  // W_M^(j2 k1) = W_N^(2 j2 k1)
+        p.T[(int64_t)row * p.B + j2] = v;
+    }
+}
+
+// ------------------------------------------------------------- k_fft_mid --
+// CTA c handles frequency rows k1 = c and A - c (c = 0 and c = A/2 are self-paired).
+__global__ void __launch_bounds__(kFftThreads) k_fft_mid(FftParams p) {
+    extern __shared__ float2 sm[];
+    const int tid = threadIdx.x;
+    const int k1a = blockIdx.x;
+    const int k1b = (p.A - k1a) % p.A;
+    const bool self = (k1a == k1b);
+    const int nrows = self ? 1 : 2;
+    const int rowa = __ldg(p.posA + k1a), rowb = __ldg(p.posA + k1b);
+    const int rs = row_padded(p.B);
+    const RowLayout lay{rs};
+    for (int e = tid; e < nrows * p.B; e += kFftThreads) {
+        const int r = e / p.B, i = e - r * p.B;
+        sm[lay(r, i)] = p.T[(int64_t)(r == 0 ? rowa : rowb) * p.B + i];
+    }
+    __syncthreads();
+    fft_inplace<+1, false>(sm, lay, nrows, p.B, p.radB, p.twB, tid, kFftThreads);
+
+    // real-input unpack, |X|^2, Hermitian repack (pairs k <-> M-k), scaled by 1/M
+    const float sc = 0.5f * p.inv_scale;
+    if (!self) {
+        for (int pos = tid; pos < p.B; pos += kFftThreads) {
+            const int k2 = __ldg(p.revB + pos);
+            const int pos2 = __ldg(p.posB + (p.B - 1 - k2));
+            const int64_t k = (int64_t)k1a + (int64_t)p.A * k2;
+            const float2 zk = sm[lay(0, pos)], zm = sm[lay(1, pos2)];
+            const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+            const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+            const float2 w = twiddle_n(p, k);
+            const float2 wO = cmul(w, O);
+            const float2 xp = cadd(E, wO), xm = csub(E, wO);
+            const float P = fmaf(xp.x, xp.x, xp.y * xp.y), Pm = fmaf(xm.x, xm.x, xm.y * xm.y);
+            const float S = (P + Pm) * sc, D = (P - Pm) * sc;
+            // Y[k] = S + i conj(w) D ; Y[M-k] = S + i w D
+            sm[lay(0, pos)] = make_float2(S + w.y * D, w.x * D);
+            sm[lay(1, pos2)] = make_float2(S - w.y * D, w.x * D);
+        }
+    } else if (k1a == 0) {
+        for (int k2 = tid; k2 <= p.B / 2; k2 += kFftThreads) {
+            const int pos = __ldg(p.posB + k2);
+            if (k2 == 0) {
+                const float2 z = sm[lay(0, pos)];
+                const float P0 = (z.x + z.y) * (z.x + z.y), PM = (z.x - z.y) * (z.x - z.y);
+                sm[lay(0, pos)] = make_float2((P0 + PM) * sc, (P0 - PM) * sc);
+                continue;
+            }
+            const int pos2 = __ldg(p.posB + (p.B - k2));
+            const int64_t k = (int64_t)p.A * k2;
+            const float2 zk = sm[lay(0, pos)], zm = sm[lay(0, pos2)];
+            const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+            const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+            const float2 w = twiddle_n(p, k);
+            const float2 wO = cmul(w, O);
+            const float2 xp = cadd(E, wO), xm = csub(E, wO);
+            const float P = fmaf(xp.x, xp.x, xp.y * xp.y), Pm = fmaf(xm.x, xm.x, xm.y * xm.y);
+            const float S = (P + Pm) * sc, D = (P - Pm) * sc;
+            sm[lay(0, pos)] = make_float2(S + w.y * D, w.x * D);
+            if (pos2 != pos) sm[lay(0, pos2)] = make_float2(S - w.y * D, w.x * D);
+        }
+    } else {  // k1 = A/2: k2 <-> B-1-k2
+        for (int k2 = tid; k2 < p.B / 2; k2 += kFftThreads) {
+            const int pos = __ldg(p.posB + k2), pos2 = __ldg(p.posB + (p.B - 1 - k2));
+            const int64_t k = (int64_t)k1a + (int64_t)p.A * k2;
+            const float2 zk = sm[lay(0, pos)], zm = sm[lay(0, pos2)];
+            const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+            const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+            const float2 w = twiddle_n(p, k);
+            const float2 wO = cmul(w, O);
+            const float2 xp = cadd(E, wO), xm = csub(E, wO);
+            const float P = fmaf(xp.x, xp.x, xp.y * xp.y), Pm = fmaf(xm.x, xm.x, xm.y * xm.y);
+            const float S = (P + Pm) * sc, D = (P - Pm) * sc;
+            sm[lay(0, pos)] = make_float2(S + w.y * D, w.x * D);
+            sm[lay(0, pos2)] = make_float2(S - w.y * D, w.x * D);
+        }
+    }
+    __syncthreads();
+    fft_inplace<-1, false>(sm, lay, nrows, p.B, p.radB, p.twB, tid, kFftThreads);
+    // U[row][j2] = y * W_M^(-j2 k1)
+    for (int e = tid; e < nrows * p.B; e += kFftThreads) {
+        const int r = e / p.B, j2 = e - r * p.B;
+        const int k1 = r == 0 ? k1a : k1b;
+        float2 v = sm[lay(r, j2)];
+        v = cmul(v, cconj(twiddle_n(p, 2 * (int64_t)j2 * k1)));
+        p.U[(int64_t)(r == 0 ? rowa : rowb) * p.B + j2] = v;
+    }
+}
+
+// ----------------------------------------------------------- k_ifft_cols --
+// U[row][j2] -> A-point inverse FFT over rows -> y[j1*B + j2] = r[2j] + i r[2j+1]
+// -> epilogue over the requested lags.
+__global__ void __launch_bounds__(kFftThreads) k_ifft_cols(FftParams p) {
+    extern __shared__ float2 sm[];
+    const int tid = threadIdx.x;
+    const int j2_0 = blockIdx.x * p.C;
+    const ColLayout lay{p.C};
+    const int total = p.A * p.C;
+    for (int e = tid; e < total; e += kFftThreads) {
+        const int row = e / p.C, col = e - row * p.C;
+        sm[lay(col, row)] = p.U[(int64_t)row * p.B + j2_0 + col];
+    }
+    __syncthreads();
+    fft_inplace<-1, true>(sm, lay, p.C, p.A, p.radA, p.twA, tid, kFftThreads);
+    for (int e = tid; e < total; e += kFftThreads) {
+        const int j1 = e / p.C, col = e - j1 * p.C;
+        const int64_t j = (int64_t)j1 * p.B + j2_0 + col;
+        const int64_t m0 = 2 * j;
+        if (m0 > p.m_hi || m0 + 1 < p.m_lo) continue;
+        const float2 v = sm[lay(col, j1)];
+        float a = v.x, b = v.y;
+        if (!p.raw) {
+            a = a * a; b = b * b;  // abs2 of the (real) correlation
+            if (p.log_scale) { a = 10.0f * log10f(a); b = 10.0f * log10f(b); }
+        }
+        if (m0 >= p.m_lo && m0 <= p.m_hi) p.out[m0 - p.m_lo] = a;
+        if (m0 + 1 >= p.m_lo && m0 + 1 <= p.m_hi) p.out[m0 + 1 - p.m_lo] = b;
+    }
+}
+
+// circular lags of a length-n signal from the linear lags of its zero-padded transform
+__global__ void __launch_bounds__(256) k_fold_lags(const float* __restrict__ lin, int64_t n, int64_t m_lo, int64_t count,
+                                                   int log_scale, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= count) return;
+    const int64_t m = m_lo + i;
+    float r = lin[m];
+    if (m > 0) r += lin[n - m];
+    float v = r * r;
+    if (log_scale) v = 10.0f * log10f(v);
+    out[i] = v;
+}
+
+}  // namespace tsdr
+
+using namespace tsdr;
+
+struct tsdr_autocorr_plan {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    size_t n;        // signal length
+    size_t N;        // transform length (power of two)
+    bool fold;
+    FftParams fp;
+    size_t smem_cols, smem_mid;
+    uint64_t launches;
+    void* d_tables;  // one allocation for every table
+    float2* d_T; float2* d_U;
+    float* d_lin;    // fold path: linear lags 0..n
+};
+
+namespace tsdr {
+
+static Radices make_radices(int len) {
+    Radices r; r.n = 0;
+    int bits = 0; while ((1 << bits) < len) ++bits;
+    const int rem = bits % 4;
+    if (rem) r.r[r.n++] = 1 << rem;
+    for (int i = 0; i < bits / 4; ++i) r.r[r.n++] = 16;
+    return r;
+}
+
+// position (after the in-place DIF) -> frequency index
+static int dif_frequency(int pos, int len, const Radices& rad) {
+    int k = 0, weight = 1, span = len;
+    for (int i = 0; i < rad.n; ++i) {
+        span /= rad.r[i];
+        const int digit = (pos / span) % rad.r[i];
+        k += digit * weight;
+        weight *= rad.r[i];
+    }
+    return k;
+}
+
+static bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
+
+}  // namespace tsdr
+
+extern "C" {
+
+int tsdr_autocorr_plan_destroy(tsdr_autocorr_plan* p) {
+    if (!p) return TSDR_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    cudaFree(p->d_tables); cudaFree(p->d_T); cudaFree(p->d_U); cudaFree(p->d_lin);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return TSDR_OK;
+}
+
+int tsdr_autocorr_plan_create(tsdr_autocorr_plan** out, int device, size_t n, void* stream) {
+    TSDR_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    TSDR_REQUIRE(n >= 2, "autocorrelation needs at least 2 samples");
+    TSDR_REQUIRE(n <= ((size_t)1 << 27), "signal too long (max 2^27 samples)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("no CUDA device available; libtempest_b200 has no CPU fallback"); return TSDR_ERR_CUDA; }
+    TSDR_REQUIRE(device >= 0 && device < ndev, "device %d out of range", device);
+    tsdr_autocorr_plan* p = new (std::nothrow) tsdr_autocorr_plan();
+    if (!p) return TSDR_ERR_NOMEM;
+    memset(p, 0, sizeof(*p));
+    p->device = device; p->n = n;
+    // direct circular transform for powers of two >= 64, zero-pad + fold otherwise
+    if (is_pow2(n) && n >= 64) { p->N = n; p->fold = false; }
+    else { size_t N = 64; while (N < 2 * n) N <<= 1; p->N = N; p->fold = true; }
+    const int64_t M = (int64_t)(p->N / 2);
+    int B = M >= ((int64_t)1 << 24) ? 8192 : 4096;
+    if ((int64_t)B > M / 2) B = (int)(M / 2);
+    const int A = (int)(M / B);
+    int C = 8;
+    while (C > 1 && (size_t)col_padded(A * C) * sizeof(float2) > 200 * 1024) C >>= 1;
+    if (C > B) C = B;
+    FftParams& fp = p->fp;
+    fp.A = A; fp.B = B; fp.C = C; fp.M = M;
+    fp.radA = make_radices(A); fp.radB = make_radices(B);
+    fp.inv_scale = 1.0f / (float)M;
+    fp.lo_bits = 12;
+    const size_t LO = (size_t)1 << fp.lo_bits;
+    const size_t HI = (p->N + LO - 1) / LO;
+    // host tables (double precision phases rounded once to float)
+    std::vector<float2> twA(A), twB(B), wlo(LO), whi(HI);
+    std::vector<int> revA(A), posA(A), revB(B), posB(B);
+    const double PI2 = 6.283185307179586476925286766559;
+    for (int k = 0; k < A; ++k) { twA[k].x = (float)cos(PI2 * k / A); twA[k].y = (float)-sin(PI2 * k / A); }
+    for (int k = 0; k < B; ++k) { twB[k].x = (float)cos(PI2 * k / B); twB[k].y = (float)-sin(PI2 * k / B); }
+    for (size_t t = 0; t < LO; ++t) { wlo[t].x = (float)cos(PI2 * (double)t / (double)p->N); wlo[t].y = (float)-sin(PI2 * (double)t / (double)p->N); }
+    for (size_t t = 0; t < HI; ++t) { const double ph = PI2 * (double)(t * LO) / (double)p->N; whi[t].x = (float)cos(ph); whi[t].y = (float)-sin(ph); }
+    for (int i = 0; i < A; ++i) { revA[i] = dif_frequency(i, A, fp.radA); posA[revA[i]] = i; }
+    for (int i = 0; i < B; ++i) { revB[i] = dif_frequency(i, B, fp.radB); posB[revB[i]] = i; }
+
+    int rc = TSDR_OK;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        if (stream) { p->stream = (cudaStream_t)stream; p->own_stream = false; }
+        else { e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking); p->own_stream = true; }
+    }
+    const size_t bytes = (A + B + LO + HI) * sizeof(float2) + (size_t)(2 * A + 2 * B) * sizeof(int);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_tables, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_T, (size_t)M * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_U, (size_t)M * sizeof(float2));
+    if (e == cudaSuccess && p->fold) e = cudaMalloc(&p->d_lin, (n + 2) * sizeof(float));
+    if (e == cudaSuccess) {
+        char* base = (char*)p->d_tables;
+        auto put = [&](const void* src, size_t sz) { void* dst = base; if (e == cudaSuccess) e = cudaMemcpy(dst, src, sz, cudaMemcpyHostToDevice); base += sz; return dst; };
+        fp.twA = (const float2*)put(twA.data(), A * sizeof(float2));
+        fp.twB = (const float2*)put(twB.data(), B * sizeof(float2));
+        fp.wlo = (const float2*)put(wlo.data(), LO * sizeof(float2));
+        fp.whi = (const float2*)put(whi.data(), HI * sizeof(float2));
+        fp.revA = (const int*)put(revA.data(), A * sizeof(int));
+        fp.posA = (const int*)put(posA.data(), A * sizeof(int));
+        fp.revB = (const int*)put(revB.data(), B * sizeof(int));
+        fp.posB = (const int*)put(posB.data(), B * sizeof(int));
+    }
+    fp.T = p->d_T; fp.U = p->d_U;
+    p->smem_cols = (size_t)col_padded(A * C) * sizeof(float2);
+    p->smem_mid = (size_t)2 * row_padded(B) * sizeof(float2);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cols);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ifft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cols);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fft_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_mid);
+    if (e != cudaSuccess) rc = cuda_fail(e, "tsdr_autocorr_plan_create", __FILE__, __LINE__);
+    if (rc != TSDR_OK) { tsdr_autocorr_plan_destroy(p); return rc; }
+    *out = p;
+    return TSDR_OK;
+}
+
+int tsdr_autocorr_plan_exec(tsdr_autocorr_plan* p, const float* x_dev, size_t index_min, size_t index_max,
+                            int log_scale, float* out_dev) {
+    TSDR_REQUIRE(p && x_dev && out_dev, "NULL argument");
+    TSDR_REQUIRE(index_min >= 1 && index_max >= index_min, "need 1 <= indexMin <= indexMax");
+    if (index_max > p->n) { set_error("BoundsError: indexMax %zu beyond the %zu-point correlation", index_max, p->n); return TSDR_ERR_BOUNDS; }
+    TSDR_REQUIRE((reinterpret_cast<uintptr_t>(x_dev) & 7) == 0, "input must be 8-byte aligned");
+    TSDR_CUDA(cudaSetDevice(p->device));
+    FftParams fp = p->fp;
+    fp.x = x_dev; fp.n_valid = (int64_t)p->n; fp.log_scale = log_scale;
+    if (p->fold) { fp.out = p->d_lin; fp.m_lo = 0; fp.m_hi = (int64_t)p->n; fp.raw = 1; }
+    else { fp.out = out_dev; fp.m_lo = (int64_t)index_min - 1; fp.m_hi = (int64_t)index_max - 1; fp.raw = 0; }
+    cudaStream_t st = p->stream;
+    k_fft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
+    k_fft_mid<<<fp.A / 2 + 1, kFftThreads, p->smem_mid, st>>>(fp);
+    k_ifft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
+    p->launches += 3;
+    if (p->fold) {
+        const int64_t count = (int64_t)(index_max - index_min + 1);
+        k_fold_lags<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(p->d_lin, (int64_t)p->n, (int64_t)index_min - 1, count, log_scale, out_dev);
+        p->launches += 1;
+    }
+    TSDR_CUDA(cudaGetLastError());
+    return TSDR_OK;
+}
+
+int tsdr_autocorr_plan_launch_count(tsdr_autocorr_plan* p, uint64_t* count) {
+    TSDR_REQUIRE(p && count, "NULL argument");
+    *count = p->launches;
+    return TSDR_OK;
+}
+
+int tsdr_autocorr_out_len(size_t len, double Fs, double min_delay, double max_delay, size_t* out_len) {
+    TSDR_REQUIRE(out_len, "out_len is NULL");
+    const int64_t index_min = 1 + round_even(min_delay * Fs);  // Autocorrelations.jl:24
+    const int64_t index_max = round_even(max_delay * Fs);      // Autocorrelations.jl:25
+    TSDR_REQUIRE(index_min >= 1 && index_max >= index_min, "empty lag range (indexMin %lld, indexMax %lld)", (long long)index_min, (long long)index_max);
+    size_t n = (size_t)(2 * index_max);
+    if (len < n) n = len;                                       // :27
+    if ((size_t)index_max > n) { *out_len = 0; set_error("BoundsError: signal of %zu samples shorter than indexMax %lld", len, (long long)index_max); return TSDR_ERR_BOUNDS; }
+    *out_len = (size_t)(index_max - index_min + 1);
+    return TSDR_OK;
+}
+
+int tsdr_autocorr_f32(const float* x, size_t len, double Fs, double min_delay, double max_delay,
+                      int log_scale, float* out, size_t* out_len) {
+    TSDR_REQUIRE(x && out, "NULL buffer");
+    size_t L = 0;
+    int rc = tsdr_autocorr_out_len(len, Fs, min_delay, max_delay, &L);
+    if (out_len) *out_len = L;
+    if (rc) return rc;
+    const int64_t index_min = 1 + round_even(min_delay * Fs), index_max = round_even(max_delay * Fs);
+    size_t n = (size_t)(2 * index_max);
+    if (len < n) n = len;
+    if ((rc = ensure_device())) return rc;
+    tsdr_autocorr_plan* plan = nullptr;
+    if ((rc = tsdr_autocorr_plan_create(&plan, current_device(), n, nullptr))) return rc;
+    void *d_x = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_x, (n + 2) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, L * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, n * sizeof(float), cudaMemcpyHostToDevice, plan->stream);
+    if (e == cudaSuccess) {
+        rc = tsdr_autocorr_plan_exec(plan, (const float*)d_x, (size_t)index_min, (size_t)index_max, log_scale, (float*)d_out);
+        if (rc == TSDR_OK) e = cudaMemcpyAsync(out, d_out, L * sizeof(float), cudaMemcpyDeviceToHost, plan->stream);
+        if (rc == TSDR_OK && e == cudaSuccess) e = cudaStreamSynchronize(plan->stream);
+    }
+    if (e != cudaSuccess && rc == TSDR_OK) rc = cuda_fail(e, "tsdr_autocorr_f32", __FILE__, __LINE__);
+    cudaFree(d_x); cudaFree(d_out);
+    tsdr_autocorr_plan_destroy(plan);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,253 @@
+"""GPU parity tests: the CUDA path (through the C ABI / Python host mirror) against the
+oracle on the same seeded inputs.  Bars: bit-exact for everything the
+oracle pins in Float32/FP64 (envelope, resampling, projections, FIR, beta, offsets, EMA);
+stated tolerances for atan2 / log10 / FFT based results."""
+import numpy as np
+import pytest
+
+import orc
+import tempestsdr_b200 as tsdr
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_iq(n, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return ((rng.normal(size=n) + 1j * rng.normal(size=n)) * scale).astype(np.complex64)
+
+
+# ---------------------------------------------------------------- Demodulation
+@pytest.mark.parametrize("n", [1, 2, 3, 1000, 65537, 1 << 20])
+def test_amDemod_bit_exact(n):
+    z = _rand_iq(n, n)
+    assert np.array_equal(tsdr.amDemod(z), orc.amDemod(z))
+
+
+def test_amDemod_special_values():
+    z = np.array([0, 1e-30 + 1e-30j, 1e30 + 1e30j, 3e38 + 1j, np.inf + 1j, 1 + 1e-9j, -3 - 4j, 1e-45 + 0j],
+                 dtype=np.complex64)
+    got, ref = tsdr.amDemod(z), orc.amDemod(z)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert got[6] == 5.0
+
+
+def test_amDemod_empty():
+    assert tsdr.amDemod(np.zeros(0, np.complex64)).size == 0
+
+
+def test_abs2_invert_fm():
+    z = _rand_iq(100003, 7)
+    assert np.array_equal(tsdr.abs2(z), orc.abs2(z))
+    assert np.array_equal(tsdr.invert_amDemod(z), orc.invert_amDemod(z))
+    # atan2: CUDA vs glibc differ by a few ulp; tolerance 4 ulp of pi
+    np.testing.assert_allclose(tsdr.fmDemod(z), orc.fmDemod(z), rtol=0, atol=4 * np.spacing(np.float32(np.pi)))
+    assert tsdr.fmDemod(z)[0] == 0.0
+
+
+# ------------------------------------------------------------------- Resampler
+@pytest.mark.parametrize("S,y_t,x_t", [(3333, 125, 200), (33333, 125, 200), (25000, 125, 200), (4000, 37, 41), (777, 30, 40)])
+def test_sig_to_image_bit_exact(S, y_t, x_t):
+    sig = np.random.default_rng(S).random(S).astype(np.float32)
+    got = tsdr.sig_to_image(sig, y_t, x_t)
+    assert got.shape == (y_t, x_t)
+    assert np.array_equal(got, orc.sig_to_image(sig, y_t, x_t))
+
+
+@pytest.mark.parametrize("y_t,x_t", [(1125, 2576), (525, 800), (600, 800), (601, 799), (300, 1000), (2250, 4400)])
+def test_downgradeImage_bit_exact(y_t, x_t):
+    img = np.random.default_rng(y_t).random((y_t, x_t)).astype(np.float32)
+    got = tsdr.downgradeImage(img)
+    assert got.shape == (600, 800)
+    assert np.array_equal(got, orc.downgradeImage(img))
+
+
+def test_naiveResampler():
+    s = np.arange(1000, dtype=np.float32)
+    out = np.zeros(3000, np.float32)
+    tsdr.naiveResampler(out, s, 3)
+    assert np.array_equal(out, orc.naiveResampler(s, 3))
+
+
+def test_fullScale_findmax():
+    m = np.random.default_rng(3).normal(size=(600, 800)).astype(np.float32)
+    assert np.array_equal(tsdr.fullScale(m), orc.fullScale(m))
+    v = m.ravel().copy()
+    v[[17, 4000, 99999]] = v.max() + 1  # ties: first index wins
+    val, idx = tsdr.findmax(v)
+    rv, ri = orc.findmax(v)
+    assert (val, idx) == (rv, ri) and idx == 18
+    v[5000] = np.nan
+    assert tsdr.findmax(v)[1] == 5001 == orc.findmax(v)[1]
+
+
+# ----------------------------------------------------------------------- vsync
+def _stripe_frame(seed, integer=True):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 8, size=(600, 800)).astype(np.float32) if integer else rng.random((600, 800)).astype(np.float32)
+    r0, c0 = int(rng.integers(0, 600)), int(rng.integers(0, 800))
+    rows = (np.arange(r0, r0 + 40) % 600)
+    cols = (np.arange(c0, c0 + 120) % 800)
+    img[rows, :] = 16.0 if integer else 1.5
+    img[:, cols] = 16.0 if integer else 1.5
+    return img
+
+
+@pytest.mark.parametrize("integer", [True, False])
+def test_vsync_matches_oracle_with_stale_beta_y(integer):
+    so, sg = orc.SyncXY(), tsdr.SyncXY()
+    assert (sg.wmin_y, sg.wmax_y, sg.wmin_x, sg.wmax_x) == (so.wmin_y, so.wmax_y, so.wmin_x, so.wmax_x) == (6, 150, 40, 200)
+    for k in range(4):
+        img = _stripe_frame(100 + k, integer)
+        ref = orc.vsync(img, so)
+        got = tsdr.vsync(img, sg)
+        assert got == ref
+        if k == 0:
+            assert got[0] == 1  # first call: beta_y still all zeros -> CartesianIndex(1,1)
+        assert np.array_equal(sg.beta_x, so.beta_x())
+        assert np.array_equal(sg.beta_y, so.beta_y())
+    sg.close()
+
+
+def test_vsync_nan_frame():
+    so, sg = orc.SyncXY(), tsdr.SyncXY()
+    img = _stripe_frame(5, False)
+    img[10, 20] = np.nan
+    assert tsdr.vsync(img, sg) == orc.vsync(img, so)
+    img2 = _stripe_frame(6, False)
+    assert tsdr.vsync(img2, sg) == orc.vsync(img2, so)  # NaN beta_y from the previous call decides s_y
+    sg.close()
+
+
+# ----------------------------------------------------------------------- chain
+CHAIN_CASES = [
+    # Fs, (x_t, y_t, fv), frames, alpha
+    (2.0e6, (800, 525, 60.0), 4, 0.1),      # upsampling in 1-D, y_t < 600 (clamped 2-D)
+    (2.0e6, (1056, 628, 60.0), 3, 0.3),     # typical
+    (20.0e6, (2576, 1125, 60.0), 2, 0.1),   # BASELINE cfg 2 shape
+    (8.0e6, (800, 600, 70.0), 3, 0.25),     # (600, 800): downgradeImage copies
+    (30.0e6, (832, 445, 85.0), 2, 0.0),     # 1-D downsampling (S > P), alpha = 0
+    (480000.0 * 50, (800, 600, 50.0), 2, 0.5),  # S == P: both resizes copy
+]
+
+
+@pytest.mark.parametrize("Fs,mode,frames,alpha", CHAIN_CASES)
+def test_chain_bit_exact(synth, Fs, mode, frames, alpha):
+    x_t, y_t, fv = mode
+    S = orc.frame_samples(Fs, fv)
+    n = S * frames + 17  # tail samples are dropped (GUI.jl:137)
+    cfg = tsdr.VideoMode(x_t, y_t, fv)
+    ch = tsdr.Chain(Fs, cfg, alpha=alpha, max_samples=n, publish_all=True)
+    so = orc.SyncXY()
+    acc = np.zeros((600, 800), np.float32)
+    for b in range(2):  # two buffers: EMA and the stale beta_y state carry over
+        iq = synth.make_iq(n, Fs, x_t, y_t, fv, seed=11 + b, t0=b * n)
+        acc, fr_ref, sy_ref, sx_ref = orc.chain_buffer(iq, Fs, x_t, y_t, fv, alpha, so, acc)
+        assert ch.push(iq) == frames
+        sy, sx = ch.offsets()
+        assert np.array_equal(sy, sy_ref) and np.array_equal(sx, sx_ref)
+        assert np.array_equal(ch.published(), fr_ref)
+        assert np.array_equal(ch.image(), acc)
+    ch.close()
+
+
+def test_chain_device_pointer_unaligned_and_reconfigure(synth):
+    import torch
+    Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)
+    S = orc.frame_samples(Fs, fv)
+    n = 3 * S
+    iq = synth.make_iq(n + 1, Fs, x_t, y_t, fv, seed=5)
+    dev = torch.from_numpy(iq.view(np.float32).copy()).cuda()
+    ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=0.2, max_samples=n)
+    so = orc.SyncXY()
+    acc = np.zeros((600, 800), np.float32)
+    for off in (0, 1):  # off=1: start 8 bytes into the allocation -> the non-16B-aligned kernel
+        acc, _, sy_ref, sx_ref = orc.chain_buffer(iq[off:off + n], Fs, x_t, y_t, fv, 0.2, so, acc, publish=False)
+        torch.cuda.synchronize()
+        assert ch.push_device(dev.data_ptr() + 8 * off, n) == 3
+        sy, sx = ch.offsets()
+        assert np.array_equal(sy, sy_ref) and np.array_equal(sx, sx_ref)
+        assert np.array_equal(ch.image(), acc)
+    # FLAG_CONFIG_UPDATE: new mode, state (imageOut, SyncXY) is kept
+    x2, y2, fv2 = 832, 520, 72.0
+    ch.configure(Fs, tsdr.VideoMode(x2, y2, fv2))
+    iq2 = synth.make_iq(n, Fs, x2, y2, fv2, seed=6)
+    acc, _, sy_ref, sx_ref = orc.chain_buffer(iq2, Fs, x2, y2, fv2, 0.2, so, acc, publish=False)
+    assert ch.push(iq2) == n // orc.frame_samples(Fs, fv2)
+    sy, sx = ch.offsets()
+    assert np.array_equal(sy, sy_ref) and np.array_equal(sx, sx_ref)
+    assert np.array_equal(ch.image(), acc)
+    ch.close()
+
+
+def test_chain_short_buffer_and_errors(synth):
+    Fs, cfg = 2.0e6, tsdr.VideoMode(800, 525, 60.0)
+    S = orc.frame_samples(Fs, 60.0)
+    ch = tsdr.Chain(Fs, cfg, max_samples=2 * S)
+    assert ch.push(np.zeros(S - 1, np.complex64)) == 0  # no complete frame: nothing happens
+    assert not ch.image().any()
+    with pytest.raises(tsdr.TempestError):
+        ch.push(np.zeros(2 * S + 1, np.complex64))
+    with pytest.raises(tsdr.TempestError):
+        tsdr.Chain(Fs, tsdr.VideoMode(1, 525, 60.0), max_samples=2 * S)
+    ch.close()
+
+
+# ---------------------------------------------------------------- autocorrelation
+def _periodic_power(n, period, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.random(period).astype(np.float32)
+    x = np.tile(base, n // period + 1)[:n] + 0.3 * rng.random(n).astype(np.float32)
+    return (1.0 + x).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,Fs,maxDelay", [
+    (1 << 12, 4096.0, 0.5),          # single small power of two: n = 2*indexMax
+    (1 << 16, 65536.0, 0.5),
+    (1 << 20, float(1 << 20), 0.5),
+    (3000, 3000.0, 0.5),             # not a power of two: zero-pad + fold path
+    (30000, 20000.0, 0.6),           # n = min(2*indexMax, len) = 24000
+    (100, 1000.0, 0.05),             # tiny
+])
+def test_autocorr_matches_oracle(n, Fs, maxDelay):
+    x = _periodic_power(n, 37 if n < 5000 else 1234, n)
+    ref, lags_ref = orc.calculate_autocorrelation(x, Fs, 0, maxDelay)
+    got, lags = tsdr.calculate_autocorrelation(x, Fs, 0, maxDelay)
+    assert got.shape == ref.shape and np.array_equal(lags, lags_ref)
+    near = ref > ref.max() - 60.0
+    # stated tolerance: 1e-2 dB on bins within 60 dB of the peak (Float32 FFT round-off, DC dominated)
+    assert np.max(np.abs(got[near] - ref[near])) <= 1e-2
+    assert orc.findmax(got[1:])[1] == orc.findmax(ref[1:])[1]
+    lin_ref, _ = orc.calculate_autocorrelation(x, Fs, 0, maxDelay, scale="lin")
+    lin, _ = tsdr.calculate_autocorrelation(x, Fs, 0, maxDelay, scale="lin")
+    np.testing.assert_allclose(lin, lin_ref, rtol=2e-4)
+
+
+def test_autocorr_min_delay_and_bounds():
+    x = _periodic_power(1 << 14, 321, 2)
+    Fs = 16384.0
+    ref, _ = orc.calculate_autocorrelation(x, Fs, 0.01, 0.4)
+    got, _ = tsdr.calculate_autocorrelation(x, Fs, 0.01, 0.4)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= 1e-2
+    with pytest.raises(IndexError):  # BoundsError in the reference: signal shorter than indexMax
+        tsdr.calculate_autocorrelation(x[:1000], Fs, 0, 0.5)
+
+
+def test_extract_configuration_recovers_refresh(synth):
+    # synthetic capture with known mode -> refresh peak and line count must be recovered exactly as the oracle does
+    Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)
+    iq = synth.make_iq(int(0.25 * Fs), Fs, x_t, y_t, fv, seed=21)
+    power = orc.abs2(iq)
+    rates, G, fv_hat = tsdr.extract_configuration(power, Fs)
+    Gr, _ = orc.calculate_autocorrelation(power, Fs, 0, 1 / 10)
+    rr, Gz = orc.zoom_autocorr(Gr, Fs, 50, 90)
+    pos = orc.findmax(Gz)[1]
+    assert fv_hat == 1 / (1 / rr[pos - 1])
+    assert abs(fv_hat - fv) < 0.05
+    Gg, _ = tsdr.calculate_autocorrelation(power, Fs, 0, 1 / 10)
+    y_hat = tsdr.estimate_lines(Gg, Fs, fv_hat)
+    _, Gs = orc.zoom_autocorr(Gr, Fs, fv_hat, fv_hat + 0.3)
+    m = orc.findmax(Gs[:500])[1]
+    assert y_hat == 1 / (fv_hat * (m / Fs))
+    name = list(tsdr.find_closest_configuration(y_hat, fv_hat))[0]
+    assert tsdr.allVideoConfigurations[name].refresh == 60.0
