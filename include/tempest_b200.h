@@ -138,6 +138,13 @@ int tsdr_chain_scale_accumulator(tsdr_chain* c, float factor);
 int tsdr_chain_stream(tsdr_chain* c, void** stream);
 /* kernels launched by this handle since creation (for bench.py's gpu_launches) */
 int tsdr_chain_launch_count(tsdr_chain* c, uint64_t* count);
+/* Optional per-kernel CUDA-event timing on the chain's stream.  While enabled every
+ * push records events around its kernels; tsdr_chain_kernel_times synchronises and
+ * returns the accumulated milliseconds and launch counts since the last call for
+ * stage 0 = k_render, 1 = k_project + k_sync, 2 = k_accumulate (+ carry). */
+#define TSDR_CHAIN_STAGES 3
+int tsdr_chain_set_profiling(tsdr_chain* c, int enable);
+int tsdr_chain_kernel_times(tsdr_chain* c, float ms[TSDR_CHAIN_STAGES], uint64_t pushes[1]);
 int tsdr_chain_destroy(tsdr_chain* c);
 
 /* ---------------------------------------------------------------------------

@@ -55,6 +55,8 @@ SIGNATURES = {
     "tsdr_chain_scale_accumulator": (C.c_int, [_vp, C.c_float]),
     "tsdr_chain_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "tsdr_chain_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "tsdr_chain_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "tsdr_chain_kernel_times": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "tsdr_chain_destroy": (C.c_int, [_vp]),
     "tsdr_autocorr_plan_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_size_t, _vp]),
     "tsdr_autocorr_plan_exec": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),

@@ -307,6 +307,16 @@ class Chain:
         check(_lib.load().tsdr_chain_launch_count(self._h, C.byref(v)))
         return v.value
 
+    def set_profiling(self, enable=True):
+        check(_lib.load().tsdr_chain_set_profiling(self._h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """(ms per stage [render, project+sync, accumulate], profiled pushes) since the last call"""
+        ms = (C.c_float * 3)()
+        n = C.c_uint64(0)
+        check(_lib.load().tsdr_chain_kernel_times(self._h, ms, C.byref(n)))
+        return [float(v) for v in ms], n.value
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.load().tsdr_chain_destroy(self._h)

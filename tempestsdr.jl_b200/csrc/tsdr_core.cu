@@ -532,6 +532,10 @@ struct tsdr_chain {
     unsigned long long* d_best;
     int* d_sy; int* d_sx;
     int* d_fy; double* d_dy; int* d_fx; double* d_dx;
+    // optional per-kernel event timing
+    bool profiling;
+    std::vector<cudaEvent_t>* ev_pool;   // recycled events
+    std::vector<cudaEvent_t>* ev_marks;  // 4 marks per profiled push
 };
 
 namespace tsdr {
@@ -646,14 +650,25 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     if (nb == 0) return TSDR_OK;
     TSDR_REQUIRE(nb <= c->max_frames, "buffer of %zu samples exceeds max_samples given at creation", n);
     cudaStream_t st = c->stream;
+    auto mark = [&]() {
+        if (!c->profiling) return;
+        cudaEvent_t ev;
+        if (!c->ev_pool->empty()) { ev = c->ev_pool->back(); c->ev_pool->pop_back(); }
+        else if (cudaEventCreate(&ev) != cudaSuccess) return;
+        cudaEventRecord(ev, st);
+        c->ev_marks->push_back(ev);
+    };
     RenderParams rp = c->rp;
     rp.iq = iq_dev; rp.n_ech = (int64_t)n;
+    mark();
     dim3 grid(kRenderH, nb);
     if ((reinterpret_cast<uintptr_t>(iq_dev) & 15) == 0) k_render<true><<<grid, kRenderThreads, c->smem_bytes, st>>>(rp);
     else k_render<false><<<grid, kRenderThreads, c->smem_bytes, st>>>(rp);
     c->launches += 1;
+    mark();
     const int align = !(c->flags & TSDR_CHAIN_NO_ALIGN);
     if (align) { launch_sync_stage(c->d_frames, nb, c->d_cv, c->d_ch, c->sp, st); c->launches += 2; }
+    mark();
     AccumParams ap;
     ap.frames = c->d_frames; ap.best = c->d_best; ap.acc = c->d_acc;
     ap.published = (c->flags & TSDR_CHAIN_PUBLISH_ALL) ? c->d_published : nullptr;
@@ -662,6 +677,7 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     k_accumulate<<<(kRenderN + kAccThreads - 1) / kAccThreads, kAccThreads, 0, st>>>(ap);
     c->launches += 1;
     if (align) { k_sync_carry<<<1, 256, 0, st>>>(c->d_best, nb, c->d_sy, c->d_sx); c->launches += 1; }
+    mark();
     TSDR_CUDA(cudaGetLastError());
     return TSDR_OK;
 }
@@ -683,6 +699,8 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
     if (!c) return TSDR_ERR_NOMEM;
     memset(c, 0, sizeof(*c));
     c->device = device; c->flags = flags; c->alpha = alpha; c->max_samples = max_samples;
+    c->ev_pool = new std::vector<cudaEvent_t>();
+    c->ev_marks = new std::vector<cudaEvent_t>();
     int rc = TSDR_OK;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) {
@@ -832,10 +850,37 @@ int tsdr_chain_launch_count(tsdr_chain* c, uint64_t* count) {
     return TSDR_OK;
 }
 
+int tsdr_chain_set_profiling(tsdr_chain* c, int enable) {
+    TSDR_REQUIRE(c, "chain is NULL");
+    c->profiling = enable != 0;
+    return TSDR_OK;
+}
+
+int tsdr_chain_kernel_times(tsdr_chain* c, float ms[TSDR_CHAIN_STAGES], uint64_t pushes[1]) {
+    TSDR_REQUIRE(c && ms && pushes, "NULL argument");
+    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < TSDR_CHAIN_STAGES; ++i) ms[i] = 0.f;
+    std::vector<cudaEvent_t>& m = *c->ev_marks;
+    const size_t np = m.size() / 4;
+    for (size_t k = 0; k < np; ++k)
+        for (int i = 0; i < TSDR_CHAIN_STAGES; ++i) {
+            float t = 0.f;
+            TSDR_CUDA(cudaEventElapsedTime(&t, m[4 * k + i], m[4 * k + i + 1]));
+            ms[i] += t;
+        }
+    pushes[0] = np;
+    for (cudaEvent_t ev : m) c->ev_pool->push_back(ev);
+    m.clear();
+    return TSDR_OK;
+}
+
 int tsdr_chain_destroy(tsdr_chain* c) {
     if (!c) return TSDR_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->ev_pool) { for (cudaEvent_t ev : *c->ev_pool) cudaEventDestroy(ev); delete c->ev_pool; }
+    if (c->ev_marks) { for (cudaEvent_t ev : *c->ev_marks) cudaEventDestroy(ev); delete c->ev_marks; }
     tsdr::chain_free_frames(c);
     cudaFree(c->d_iq); cudaFree(c->d_acc); cudaFree(c->d_tmp);
     cudaFree(c->d_fy); cudaFree(c->d_dy); cudaFree(c->d_fx); cudaFree(c->d_dx);
