@@ -233,7 +233,13 @@ def main():
     frames = n_ech // S
     # ring of distinct device buffers larger than L2 (126 MB): no buffer is L2-resident when its step starts
     ring = [synth.make_iq_torch(n_ech, Fs, x_t, y_t, fv, dev, seed=100 * rank + i, t0=i * n_ech) for i in range(wl["ring"])]
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) stream shared by the chain and the timing events: the
+    # legacy default stream has handle 0, which the C ABI reads as "create a private stream"
+    torch.cuda.synchronize()
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
+    assert stream != 0
     ch = tsdr.Chain(Fs, cfg, alpha=0.1, max_samples=n_ech, device=local_rank, stream=stream)
 
     def barrier():

@@ -266,13 +266,21 @@ orc_sync* orc_sync_create(int n_y, int n_x) { /* :25-48 */
 void orc_sync_destroy(orc_sync* s) { if (!s) return; free(s->beta_x); free(s->beta_y); free(s); }
 
 /* sum(image;dims=1): Julia reduces each column with a @simd loop whose
- * association is CPU dependent; this restatement FIXES the order to the plain
- * sequential one (row 1, 2, ... 600), Float32 accumulator. */
+ * association is CPU dependent (several vector accumulators, folded at the end).
+ * This restatement FIXES the association: the rows are cut into 8 consecutive
+ * blocks of ceil(n_y/8) rows, each block is summed in row order with a Float32
+ * accumulator, and the 8 partial sums are added in block order. */
 void orc_proj_cols(const float* img, int n_y, int n_x, float* c_v) {
+    const int rows_per = (n_y + 7) / 8;
     for (int j = 0; j < n_x; ++j) {
-        float acc = img[(size_t)j * n_y];
-        for (int i = 1; i < n_y; ++i) acc = acc + img[(size_t)j * n_y + i];
-        c_v[j] = acc;
+        float tot = 0.0f;
+        for (int b = 0; b * rows_per < n_y; ++b) {
+            const int r0 = b * rows_per, r1 = (r0 + rows_per < n_y) ? r0 + rows_per : n_y;
+            float acc = img[(size_t)j * n_y + r0];
+            for (int i = r0 + 1; i < r1; ++i) acc = acc + img[(size_t)j * n_y + i];
+            tot = (b == 0) ? acc : tot + acc;
+        }
+        c_v[j] = tot;
     }
 }
 

@@ -403,10 +403,10 @@ static const unsigned long long kBestInit = 0x00000000ffffffffull;  // beta = 0 
 
 static int launch_sync_stage(const float* frames, int n_frames, float* c_v, float* c_h, const SyncParams& sp,
                              cudaStream_t st) {
-    dim3 pg(kProjColBlocks + kProjRowBlocks, n_frames);
+    dim3 pg(kProjColCtas + kProjRowCtas, n_frames);
     k_project<<<pg, kProjThreads, 0, st>>>(frames, c_v, c_h);
-    dim3 sg(n_frames, 2 * kSyncSplit);
-    k_sync<<<sg, kSyncThreads, 0, st>>>(sp);
+    k_fir_sigma<<<dim3(n_frames, 2), kFirThreads, 0, st>>>(sp);
+    k_beta<<<dim3(n_frames, kBetaCtasX + kBetaCtasY), kBetaThreads, 0, st>>>(sp);
     return TSDR_OK;
 }
 
@@ -419,6 +419,7 @@ struct tsdr_sync {
     float* d_img_cm;   // staging, column-major
     float* d_img;      // scan order
     float* d_cv; float* d_ch;
+    float* d_cfv; float* d_cfh; float* d_sigma;
     float* d_beta_x; float* d_beta_y;
     unsigned long long* d_best;  // [2][2]
     int* d_off;                  // [2]
@@ -446,6 +447,9 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     if (e == cudaSuccess) e = cudaMalloc(&s->d_img, (size_t)kRenderN * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cv, n_x * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_ch, n_y * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_cfv, n_x * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_cfh, n_y * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_sigma, 2 * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_beta_x, nbx * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_beta_y, nby * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_best, 4 * 8);
@@ -456,6 +460,7 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     if (e == cudaSuccess) e = cudaMemcpy(s->d_best, init, sizeof(init), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { tsdr_sync_destroy(s); return cuda_fail(e, "tsdr_sync_create", __FILE__, __LINE__); }
     sp.c_v = s->d_cv; sp.c_h = s->d_ch; sp.best = s->d_best; sp.beta_x = s->d_beta_x; sp.beta_y = s->d_beta_y;
+    sp.cf_v = s->d_cfv; sp.cf_h = s->d_cfh; sp.sigma = s->d_sigma;
     *out = s;
     return TSDR_OK;
 }
@@ -498,6 +503,7 @@ int tsdr_sync_destroy(tsdr_sync* s) {
     if (!s) return TSDR_OK;
     cudaSetDevice(s->device);
     cudaFree(s->d_img_cm); cudaFree(s->d_img); cudaFree(s->d_cv); cudaFree(s->d_ch);
+    cudaFree(s->d_cfv); cudaFree(s->d_cfh); cudaFree(s->d_sigma);
     cudaFree(s->d_beta_x); cudaFree(s->d_beta_y); cudaFree(s->d_best); cudaFree(s->d_off);
     delete s;
     return TSDR_OK;
@@ -529,9 +535,10 @@ struct tsdr_chain {
     float* d_acc;       // imageOut, scan order
     float* d_tmp;       // 600x800 transpose target
     float* d_cv; float* d_ch;
+    float* d_cfv; float* d_cfh; float* d_sigma;
     unsigned long long* d_best;
     int* d_sy; int* d_sx;
-    int* d_fy; double* d_dy; int* d_fx; double* d_dx;
+    int* d_fy; double* d_dy; double* d_kd; double* d_dx;
     // optional per-kernel event timing
     bool profiling;
     std::vector<cudaEvent_t>* ev_pool;   // recycled events
@@ -555,6 +562,9 @@ static void chain_free_frames(tsdr_chain* c) {
     cudaFree(c->d_published); c->d_published = nullptr;
     cudaFree(c->d_cv); c->d_cv = nullptr;
     cudaFree(c->d_ch); c->d_ch = nullptr;
+    cudaFree(c->d_cfv); c->d_cfv = nullptr;
+    cudaFree(c->d_cfh); c->d_cfh = nullptr;
+    cudaFree(c->d_sigma); c->d_sigma = nullptr;
     cudaFree(c->d_best); c->d_best = nullptr;
     cudaFree(c->d_sy); c->d_sy = nullptr;
     cudaFree(c->d_sx); c->d_sx = nullptr;
@@ -611,6 +621,9 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         if (c->flags & TSDR_CHAIN_PUBLISH_ALL) TSDR_CUDA(cudaMalloc(&c->d_published, (size_t)max_frames * kRenderN * 4));
         TSDR_CUDA(cudaMalloc(&c->d_cv, (size_t)max_frames * kRenderW * 4));
         TSDR_CUDA(cudaMalloc(&c->d_ch, (size_t)max_frames * kRenderH * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_cfv, (size_t)max_frames * kRenderW * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_cfh, (size_t)max_frames * kRenderH * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_sigma, (size_t)max_frames * 2 * 4));
         TSDR_CUDA(cudaMalloc(&c->d_best, (size_t)(max_frames + 1) * 2 * 8));
         TSDR_CUDA(cudaMalloc(&c->d_sy, (size_t)max_frames * 4));
         TSDR_CUDA(cudaMalloc(&c->d_sx, (size_t)max_frames * 4));
@@ -620,7 +633,9 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     }
     TSDR_CUDA(cudaMemcpyAsync(c->d_fy, fy.data(), kRenderH * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     TSDR_CUDA(cudaMemcpyAsync(c->d_dy, dy.data(), kRenderH * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    TSDR_CUDA(cudaMemcpyAsync(c->d_fx, fx.data(), kRenderW * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    std::vector<double> kd(kRenderW);
+    for (int j = 0; j < kRenderW; ++j) kd[j] = (double)fx[j];
+    TSDR_CUDA(cudaMemcpyAsync(c->d_kd, kd.data(), kRenderW * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     TSDR_CUDA(cudaMemcpyAsync(c->d_dx, dx.data(), kRenderW * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     TSDR_CUDA(cudaStreamSynchronize(c->stream));  // the std::vectors die at return
 
@@ -629,17 +644,28 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     RenderParams& rp = c->rp;
     rp.S = S; rp.x_t = x_t; rp.y_t = y_t;
     rp.sf1 = m1.sf; rp.off1 = m1.off; rp.clamp1 = m1.clamp; rp.identity1 = m1.identity; rp.identity2 = identity2;
-    rp.fy = c->d_fy; rp.dy = c->d_dy; rp.fx = c->d_fx; rp.dx = c->d_dx;
+    rp.fy = c->d_fy; rp.dy = c->d_dy; rp.kd = c->d_kd; rp.dx = c->d_dx;
+    // pixel range whose raw coordinate x(i) = sf*i + off already lies in [1, S): no clamp, no floor fix-up
+    {
+        auto raw = [&](double i1) { volatile double pr = m1.sf * i1; return pr + m1.off; };
+        int64_t lo = 1, hi = P;                      // smallest i with x >= 1
+        while (lo < hi) { int64_t mid = (lo + hi) / 2; if (raw((double)mid) >= 1.0) hi = mid; else lo = mid + 1; }
+        rp.safe_lo = (double)lo;
+        lo = 1; hi = P;                              // largest i with x < S
+        while (lo < hi) { int64_t mid = (lo + hi + 1) / 2; if (raw((double)mid) < (double)S) lo = mid; else hi = mid - 1; }
+        rp.safe_hi = (double)lo;
+        if (!(raw(rp.safe_lo) >= 1.0) || !(raw(rp.safe_hi) < (double)S)) { rp.safe_lo = 1.0; rp.safe_hi = 0.0; }  // every CTA takes the exact path
+    }
     rp.fx_first = fx[0]; rp.fx_last = fx[kRenderW - 1];
     rp.frames = c->d_frames; rp.win_max = win;
-    TSDR_CUDA(cudaFuncSetAttribute(k_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TSDR_CUDA(cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSDR_CUDA(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SyncParams& sp = c->sp;
     gaussian_taps(sp.h);
     sp.n_x = kRenderW; sp.n_y = kRenderH;
     sp.wmin_y = (int)ceil(1.0 / 100.0 * (double)kRenderH); sp.wmax_y = (int)floor((double)kRenderH / 4.0);
     sp.wmin_x = (int)ceil(5.0 / 100.0 * (double)kRenderW); sp.wmax_x = (int)floor((double)kRenderW / 4.0);
     sp.c_v = c->d_cv; sp.c_h = c->d_ch; sp.best = c->d_best; sp.beta_x = nullptr; sp.beta_y = nullptr;
+    sp.cf_v = c->d_cfv; sp.cf_h = c->d_cfh; sp.sigma = c->d_sigma;
     return TSDR_OK;
 }
 
@@ -662,12 +688,11 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     rp.iq = iq_dev; rp.n_ech = (int64_t)n;
     mark();
     dim3 grid(kRenderH, nb);
-    if ((reinterpret_cast<uintptr_t>(iq_dev) & 15) == 0) k_render<true><<<grid, kRenderThreads, c->smem_bytes, st>>>(rp);
-    else k_render<false><<<grid, kRenderThreads, c->smem_bytes, st>>>(rp);
+    k_render<<<grid, kRenderThreads, c->smem_bytes, st>>>(rp);
     c->launches += 1;
     mark();
     const int align = !(c->flags & TSDR_CHAIN_NO_ALIGN);
-    if (align) { launch_sync_stage(c->d_frames, nb, c->d_cv, c->d_ch, c->sp, st); c->launches += 2; }
+    if (align) { launch_sync_stage(c->d_frames, nb, c->d_cv, c->d_ch, c->sp, st); c->launches += 3; }
     mark();
     AccumParams ap;
     ap.frames = c->d_frames; ap.best = c->d_best; ap.acc = c->d_acc;
@@ -712,7 +737,7 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tmp, (size_t)kRenderN * 4);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_fy, kRenderH * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_dy, kRenderH * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_fx, kRenderW * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_kd, kRenderW * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_dx, kRenderW * sizeof(double));
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_acc, 0, (size_t)kRenderN * 4, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_iq, 0, (max_samples + 2) * 8, c->stream);
@@ -883,7 +908,7 @@ int tsdr_chain_destroy(tsdr_chain* c) {
     if (c->ev_marks) { for (cudaEvent_t ev : *c->ev_marks) cudaEventDestroy(ev); delete c->ev_marks; }
     tsdr::chain_free_frames(c);
     cudaFree(c->d_iq); cudaFree(c->d_acc); cudaFree(c->d_tmp);
-    cudaFree(c->d_fy); cudaFree(c->d_dy); cudaFree(c->d_fx); cudaFree(c->d_dx);
+    cudaFree(c->d_fy); cudaFree(c->d_dy); cudaFree(c->d_kd); cudaFree(c->d_dx);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return TSDR_OK;
