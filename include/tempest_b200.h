@@ -147,6 +147,11 @@ int tsdr_chain_set_profiling(tsdr_chain* c, int enable);
 int tsdr_chain_kernel_times(tsdr_chain* c, float ms[TSDR_CHAIN_STAGES], uint64_t pushes[1]);
 int tsdr_chain_destroy(tsdr_chain* c);
 
+/* Diagnostic: evaluates abs(::ComplexF32) on n pseudo-random operand pairs (seeded) twice,
+ * once with the kernels' guard-free fast path and once with the IEEE intrinsics only
+ * (__fsqrt_rn / __fdiv_rn), and reports how many results differ in any bit. */
+int tsdr_selftest_hypot(uint64_t n, uint64_t seed, uint64_t* mismatches);
+
 /* ---------------------------------------------------------------------------
  * Device-resident autocorrelation plan (the measured M2 path): input already
  * in HBM, Stockham FFT -> |X|^2 -> inverse -> 10log10|.|^2 of the lag slice.

@@ -135,9 +135,9 @@ def seq_sum(a, axis=0):
 
 
 def col_sum_blocked(img):
-    """sum(image;dims=1) with the oracle's fixed association: 8 blocks of ceil(n_y/8) rows."""
+    """sum(image;dims=1) with the oracle's fixed association: bands of 32 rows, folded in order."""
     img = np.asarray(img, np.float32)
-    rows_per = (img.shape[0] + 7) // 8
+    rows_per = 32
     tot = None
     for r0 in range(0, img.shape[0], rows_per):
         part = seq_sum(img[r0:r0 + rows_per], axis=0)
@@ -195,7 +195,7 @@ class SyncXY:
 
 def vsync(img, s):  # src/FrameSynchronisation.jl:56-79
     img = np.asarray(img, np.float32)
-    c_v = filt5(s.h, col_sum_blocked(img))   # column sums: 8 row blocks, see tsdr_oracle.c:orc_proj_cols
+    c_v = filt5(s.h, col_sum_blocked(img))   # column sums: 32-row bands, see tsdr_oracle.c:orc_proj_cols
     s.beta_x = fill_beta(c_v, s.wmin_x, s.wmax_x)
     s_y = argmax_col(s.beta_y)               # stale beta_y (previous call)
     c_h = filt5(s.h, seq_sum(img, axis=1))   # row sums, columns added in order

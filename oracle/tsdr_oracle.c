@@ -267,18 +267,19 @@ void orc_sync_destroy(orc_sync* s) { if (!s) return; free(s->beta_x); free(s->be
 
 /* sum(image;dims=1): Julia reduces each column with a @simd loop whose
  * association is CPU dependent (several vector accumulators, folded at the end).
- * This restatement FIXES the association: the rows are cut into 8 consecutive
- * blocks of ceil(n_y/8) rows, each block is summed in row order with a Float32
- * accumulator, and the 8 partial sums are added in block order. */
+ * This restatement FIXES the association: the rows are cut into consecutive
+ * bands of 32 rows (19 bands for 600 rows, the last one short), each band is
+ * summed in row order with a Float32 accumulator, and the band partials are
+ * added in band order. */
+#define ORC_BAND_ROWS 32
 void orc_proj_cols(const float* img, int n_y, int n_x, float* c_v) {
-    const int rows_per = (n_y + 7) / 8;
     for (int j = 0; j < n_x; ++j) {
         float tot = 0.0f;
-        for (int b = 0; b * rows_per < n_y; ++b) {
-            const int r0 = b * rows_per, r1 = (r0 + rows_per < n_y) ? r0 + rows_per : n_y;
+        for (int r0 = 0; r0 < n_y; r0 += ORC_BAND_ROWS) {
+            const int r1 = (r0 + ORC_BAND_ROWS < n_y) ? r0 + ORC_BAND_ROWS : n_y;
             float acc = img[(size_t)j * n_y + r0];
             for (int i = r0 + 1; i < r1; ++i) acc = acc + img[(size_t)j * n_y + i];
-            tot = (b == 0) ? acc : tot + acc;
+            tot = (r0 == 0) ? acc : tot + acc;
         }
         c_v[j] = tot;
     }

@@ -58,6 +58,7 @@ SIGNATURES = {
     "tsdr_chain_set_profiling": (C.c_int, [_vp, C.c_int]),
     "tsdr_chain_kernel_times": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "tsdr_chain_destroy": (C.c_int, [_vp]),
+    "tsdr_selftest_hypot": (C.c_int, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "tsdr_autocorr_plan_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_size_t, _vp]),
     "tsdr_autocorr_plan_exec": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),
     "tsdr_autocorr_plan_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),

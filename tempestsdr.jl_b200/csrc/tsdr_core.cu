@@ -391,6 +391,50 @@ int tsdr_findmax_f32(const float* v, size_t n, float* value, size_t* index1) {
 }  // extern "C"
 
 namespace tsdr {
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& x) {
+    unsigned long long z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) k_selftest_hypot(unsigned long long n, unsigned long long seed, unsigned long long* bad) {
+    unsigned long long local = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256) {
+        unsigned long long st = seed + i * 0x2545f4914f6cdd1dull;
+        const unsigned long long a = splitmix64(st), b = splitmix64(st);
+        // mode 0: any bit patterns; 1: both magnitudes inside the fast range; 2: close exponents
+        const int mode = (int)(b >> 62);
+        unsigned int xb = (unsigned int)a, yb = (unsigned int)(a >> 32);
+        if (mode >= 1) {
+            const unsigned int ex = 117u + (unsigned int)((b & 0xffff) % 50u);           // 2^-10 .. 2^39
+            const unsigned int ey = mode == 2 ? ex - (unsigned int)((b >> 16) % 13u) : 117u + (unsigned int)((b >> 16) % 50u);
+            xb = (xb & 0x807fffffu) | (ex << 23);
+            yb = (yb & 0x807fffffu) | (ey << 23);
+        }
+        const float x = __uint_as_float(xb), y = __uint_as_float(yb);
+        const float f = dev_hypotf(x, y), g = dev_hypotf_ieee(x, y);
+        const bool same = (__float_as_uint(f) == __float_as_uint(g)) || (f != f && g != g);
+        local += same ? 0 : 1;
+    }
+    if (local) atomicAdd(bad, local);
+}
+}  // namespace tsdr
+
+extern "C" int tsdr_selftest_hypot(uint64_t n, uint64_t seed, uint64_t* mismatches) {
+    TSDR_REQUIRE(mismatches, "mismatches is NULL");
+    int rc = ensure_device(); if (rc) return rc;
+    void* d = nullptr;
+    if ((rc = scratch(3, 8, &d))) return rc;
+    TSDR_CUDA(cudaMemset(d, 0, 8));
+    k_selftest_hypot<<<148 * 8, 256>>>(n, seed, (unsigned long long*)d);
+    TSDR_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    TSDR_CUDA(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+    *mismatches = h;
+    return TSDR_OK;
+}
+
+namespace tsdr {
 
 static void gaussian_taps(float h[5]) {  // init_gaussian_filter(5) then convert to Float32 (new{T})
     double g[5], sum = 0.0;
@@ -403,8 +447,7 @@ static const unsigned long long kBestInit = 0x00000000ffffffffull;  // beta = 0 
 
 static int launch_sync_stage(const float* frames, int n_frames, float* c_v, float* c_h, const SyncParams& sp,
                              cudaStream_t st) {
-    dim3 pg(kProjColCtas + kProjRowCtas, n_frames);
-    k_project<<<pg, kProjThreads, 0, st>>>(frames, c_v, c_h);
+    k_project<<<dim3(kBands, n_frames), kProjThreads, kProjSmem, st>>>(frames, c_v, c_h);
     k_fir_sigma<<<dim3(n_frames, 2), kFirThreads, 0, st>>>(sp);
     k_beta<<<dim3(n_frames, kBetaCtasX + kBetaCtasY), kBetaThreads, 0, st>>>(sp);
     return TSDR_OK;
@@ -445,7 +488,8 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&s->d_img_cm, (size_t)kRenderN * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_img, (size_t)kRenderN * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_cv, n_x * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_cv, (size_t)kBands * n_x * 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProjSmem);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_ch, n_y * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cfv, n_x * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cfh, n_y * 4);
@@ -459,7 +503,7 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     const unsigned long long init[4] = {0ull, kBestInit, 0ull, 0ull};
     if (e == cudaSuccess) e = cudaMemcpy(s->d_best, init, sizeof(init), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { tsdr_sync_destroy(s); return cuda_fail(e, "tsdr_sync_create", __FILE__, __LINE__); }
-    sp.c_v = s->d_cv; sp.c_h = s->d_ch; sp.best = s->d_best; sp.beta_x = s->d_beta_x; sp.beta_y = s->d_beta_y;
+    sp.colpart = s->d_cv; sp.c_h = s->d_ch; sp.best = s->d_best; sp.beta_x = s->d_beta_x; sp.beta_y = s->d_beta_y;
     sp.cf_v = s->d_cfv; sp.cf_h = s->d_cfh; sp.sigma = s->d_sigma;
     *out = s;
     return TSDR_OK;
@@ -538,7 +582,7 @@ struct tsdr_chain {
     float* d_cfv; float* d_cfh; float* d_sigma;
     unsigned long long* d_best;
     int* d_sy; int* d_sx;
-    int* d_fy; double* d_dy; double* d_kd; double* d_dx;
+    int* d_fy; double* d_dy; double* d_kd; double* d_dx; int* d_win_lo; int* d_win_len;
     // optional per-kernel event timing
     bool profiling;
     std::vector<cudaEvent_t>* ev_pool;   // recycled events
@@ -595,6 +639,7 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     }
     // largest shared-memory window over the 600 output rows
     int win = 0;
+    std::vector<int> win_lo(kRenderH), win_len(kRenderH);
     for (int i = 0; i < kRenderH; ++i) {
         const double i_lo = (double)((int64_t)fy[i] * x_t + fx[0] + 1);
         const double i_hi = identity2 ? (double)((int64_t)fy[i] * x_t + fx[kRenderW - 1] + 1)
@@ -603,9 +648,10 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         if (m1.identity) { flo = i_lo; fhi = i_hi - 1.0; }
         else { host_coord(m1.sf, m1.off, i_lo, m1.clamp, (double)S, flo, t); host_coord(m1.sf, m1.off, i_hi, m1.clamp, (double)S, fhi, t); }
         const int W = (int)(fhi - flo) + 2;
+        win_lo[i] = (int)flo; win_len[i] = W;
         if (W > win) win = W;
     }
-    const size_t smem = (size_t)(win + 4) * sizeof(float);
+    const size_t smem = (size_t)(win + 4) * sizeof(double);
     if (smem > 200 * 1024) {
         set_error("frame window of %d samples does not fit shared memory (Fs/fv/y_t = %.1f samples per line)", win,
                   (double)S / y_t);
@@ -619,7 +665,7 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         chain_free_frames(c);
         TSDR_CUDA(cudaMalloc(&c->d_frames, (size_t)max_frames * kRenderN * 4));
         if (c->flags & TSDR_CHAIN_PUBLISH_ALL) TSDR_CUDA(cudaMalloc(&c->d_published, (size_t)max_frames * kRenderN * 4));
-        TSDR_CUDA(cudaMalloc(&c->d_cv, (size_t)max_frames * kRenderW * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_cv, (size_t)max_frames * kBands * kRenderW * 4));
         TSDR_CUDA(cudaMalloc(&c->d_ch, (size_t)max_frames * kRenderH * 4));
         TSDR_CUDA(cudaMalloc(&c->d_cfv, (size_t)max_frames * kRenderW * 4));
         TSDR_CUDA(cudaMalloc(&c->d_cfh, (size_t)max_frames * kRenderH * 4));
@@ -637,6 +683,8 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     for (int j = 0; j < kRenderW; ++j) kd[j] = (double)fx[j];
     TSDR_CUDA(cudaMemcpyAsync(c->d_kd, kd.data(), kRenderW * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     TSDR_CUDA(cudaMemcpyAsync(c->d_dx, dx.data(), kRenderW * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    TSDR_CUDA(cudaMemcpyAsync(c->d_win_lo, win_lo.data(), kRenderH * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    TSDR_CUDA(cudaMemcpyAsync(c->d_win_len, win_len.data(), kRenderH * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     TSDR_CUDA(cudaStreamSynchronize(c->stream));  // the std::vectors die at return
 
     c->Fs = Fs; c->fv = fv; c->x_t = x_t; c->y_t = y_t; c->S = S; c->max_frames = max_frames;
@@ -644,7 +692,7 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     RenderParams& rp = c->rp;
     rp.S = S; rp.x_t = x_t; rp.y_t = y_t;
     rp.sf1 = m1.sf; rp.off1 = m1.off; rp.clamp1 = m1.clamp; rp.identity1 = m1.identity; rp.identity2 = identity2;
-    rp.fy = c->d_fy; rp.dy = c->d_dy; rp.kd = c->d_kd; rp.dx = c->d_dx;
+    rp.fy = c->d_fy; rp.dy = c->d_dy; rp.kd = c->d_kd; rp.dx = c->d_dx; rp.win_lo = c->d_win_lo; rp.win_len = c->d_win_len;
     // pixel range whose raw coordinate x(i) = sf*i + off already lies in [1, S): no clamp, no floor fix-up
     {
         auto raw = [&](double i1) { volatile double pr = m1.sf * i1; return pr + m1.off; };
@@ -657,14 +705,15 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         if (!(raw(rp.safe_lo) >= 1.0) || !(raw(rp.safe_hi) < (double)S)) { rp.safe_lo = 1.0; rp.safe_hi = 0.0; }  // every CTA takes the exact path
     }
     rp.fx_first = fx[0]; rp.fx_last = fx[kRenderW - 1];
-    rp.frames = c->d_frames; rp.win_max = win;
+    rp.frames = c->d_frames;
     TSDR_CUDA(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSDR_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProjSmem));
     SyncParams& sp = c->sp;
     gaussian_taps(sp.h);
     sp.n_x = kRenderW; sp.n_y = kRenderH;
     sp.wmin_y = (int)ceil(1.0 / 100.0 * (double)kRenderH); sp.wmax_y = (int)floor((double)kRenderH / 4.0);
     sp.wmin_x = (int)ceil(5.0 / 100.0 * (double)kRenderW); sp.wmax_x = (int)floor((double)kRenderW / 4.0);
-    sp.c_v = c->d_cv; sp.c_h = c->d_ch; sp.best = c->d_best; sp.beta_x = nullptr; sp.beta_y = nullptr;
+    sp.colpart = c->d_cv; sp.c_h = c->d_ch; sp.best = c->d_best; sp.beta_x = nullptr; sp.beta_y = nullptr;
     sp.cf_v = c->d_cfv; sp.cf_h = c->d_cfh; sp.sigma = c->d_sigma;
     return TSDR_OK;
 }
@@ -699,7 +748,7 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     ap.published = (c->flags & TSDR_CHAIN_PUBLISH_ALL) ? c->d_published : nullptr;
     ap.n_frames = nb; ap.alpha = c->alpha; ap.one_minus_alpha = 1.0f - c->alpha;
     ap.align = align; ap.sum_mode = (c->flags & TSDR_CHAIN_SUM) ? 1 : 0;
-    k_accumulate<<<(kRenderN + kAccThreads - 1) / kAccThreads, kAccThreads, 0, st>>>(ap);
+    k_accumulate<<<kRenderH, kAccThreads, 0, st>>>(ap);
     c->launches += 1;
     if (align) { k_sync_carry<<<1, 256, 0, st>>>(c->d_best, nb, c->d_sy, c->d_sx); c->launches += 1; }
     mark();
@@ -738,6 +787,8 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
     if (e == cudaSuccess) e = cudaMalloc(&c->d_fy, kRenderH * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_dy, kRenderH * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_kd, kRenderW * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_win_lo, kRenderH * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_win_len, kRenderH * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_dx, kRenderW * sizeof(double));
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_acc, 0, (size_t)kRenderN * 4, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_iq, 0, (max_samples + 2) * 8, c->stream);
@@ -908,7 +959,7 @@ int tsdr_chain_destroy(tsdr_chain* c) {
     if (c->ev_marks) { for (cudaEvent_t ev : *c->ev_marks) cudaEventDestroy(ev); delete c->ev_marks; }
     tsdr::chain_free_frames(c);
     cudaFree(c->d_iq); cudaFree(c->d_acc); cudaFree(c->d_tmp);
-    cudaFree(c->d_fy); cudaFree(c->d_dy); cudaFree(c->d_kd); cudaFree(c->d_dx);
+    cudaFree(c->d_fy); cudaFree(c->d_dy); cudaFree(c->d_kd); cudaFree(c->d_dx); cudaFree(c->d_win_lo); cudaFree(c->d_win_len);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return TSDR_OK;

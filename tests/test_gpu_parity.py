@@ -31,6 +31,15 @@ def test_amDemod_special_values():
     assert got[6] == 5.0
 
 
+def test_hypot_fast_path_matches_ieee():
+    # the kernels' guard-free sqrt / div sequences against __fsqrt_rn / __fdiv_rn on 2^32 operand pairs
+    import ctypes as C
+    from tempestsdr_b200 import _lib
+    bad = C.c_uint64(1)
+    _lib.check(_lib.load().tsdr_selftest_hypot(1 << 32, 0xB200, C.byref(bad)))
+    assert bad.value == 0
+
+
 def test_amDemod_empty():
     assert tsdr.amDemod(np.zeros(0, np.complex64)).size == 0
 
