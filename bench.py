@@ -258,6 +258,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         ch.push_device(ring[i % len(ring)].data_ptr(), n_ech)
+    ch.flush()  # the timed region ends when the last buffer's sync/accumulate kernels have finished too
     e1.record()
     torch.cuda.synchronize()
     elapsed_ms = e0.elapsed_time(e1)

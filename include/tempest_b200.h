@@ -107,6 +107,7 @@ typedef struct tsdr_chain tsdr_chain;
 #define TSDR_CHAIN_PUBLISH_ALL 1u /* keep every intermediate imageOut of the last buffer (GUI.jl:177) */
 #define TSDR_CHAIN_NO_ALIGN    2u /* do_align = false (GUI.jl:170): skip vsync/circshift */
 #define TSDR_CHAIN_SUM         4u /* plain frame sum instead of the EMA (long integrations, cfg 5) */
+#define TSDR_CHAIN_NO_OVERLAP  8u /* run every kernel on the primary stream (no two-stream pipelining) */
 
 /* stream: a cudaStream_t to run on (e.g. the caller's), or NULL for a private one. */
 int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t, double fv, float alpha,
@@ -123,6 +124,10 @@ int tsdr_chain_reset(tsdr_chain* c);
 int tsdr_chain_push_host(tsdr_chain* c, const float* iq_host, size_t n, int* n_frames);
 int tsdr_chain_push_device(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames);
 int tsdr_chain_sync(tsdr_chain* c);
+/* Make the primary stream wait (on the device, no host block) for the work the chain queued
+ * on its internal auxiliary stream: after this, an event recorded on the primary stream
+ * covers every kernel of every push so far. */
+int tsdr_chain_flush(tsdr_chain* c);
 /* imageOut (600 x 800, column-major) -> host; synchronises the stream */
 int tsdr_chain_read_image(tsdr_chain* c, float* out_colmajor);
 /* per-frame (s_y, s_x) of the last pushed buffer -> host (up to max entries) */

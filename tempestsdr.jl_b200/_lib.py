@@ -12,6 +12,7 @@ SO = os.path.join(HERE, "libtempest_b200.so")
 TSDR_CHAIN_PUBLISH_ALL = 1
 TSDR_CHAIN_NO_ALIGN = 2
 TSDR_CHAIN_SUM = 4
+TSDR_CHAIN_NO_OVERLAP = 8
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int)
@@ -48,6 +49,7 @@ SIGNATURES = {
     "tsdr_chain_push_host": (C.c_int, [_vp, _vp, C.c_size_t, _ip]),
     "tsdr_chain_push_device": (C.c_int, [_vp, _vp, C.c_size_t, _ip]),
     "tsdr_chain_sync": (C.c_int, [_vp]),
+    "tsdr_chain_flush": (C.c_int, [_vp]),
     "tsdr_chain_read_image": (C.c_int, [_vp, _vp]),
     "tsdr_chain_read_offsets": (C.c_int, [_vp, _vp, _vp, C.c_int, _ip]),
     "tsdr_chain_read_published": (C.c_int, [_vp, _vp, C.c_int, _ip]),

@@ -219,11 +219,11 @@ class Chain:
     """
 
     def __init__(self, Fs, config, alpha=0.1, max_samples=None, device=0, publish_all=False, do_align=True,
-                 sum_mode=False, stream=None):
+                 sum_mode=False, stream=None, overlap=True):
         if max_samples is None:
             max_samples = getImageDuration(config, Fs)
         flags = (_lib.TSDR_CHAIN_PUBLISH_ALL if publish_all else 0) | (0 if do_align else _lib.TSDR_CHAIN_NO_ALIGN) \
-            | (_lib.TSDR_CHAIN_SUM if sum_mode else 0)
+            | (_lib.TSDR_CHAIN_SUM if sum_mode else 0) | (0 if overlap else _lib.TSDR_CHAIN_NO_OVERLAP)
         h = C.c_void_p()
         check(_lib.load().tsdr_chain_create(C.byref(h), int(device), float(Fs), int(config.width), int(config.height),
                                             float(config.refresh), float(alpha), int(max_samples), flags,
@@ -265,6 +265,10 @@ class Chain:
 
     def sync(self):
         check(_lib.load().tsdr_chain_sync(self._h))
+
+    def flush(self):
+        """primary stream waits (device side) for the chain's auxiliary stream"""
+        check(_lib.load().tsdr_chain_flush(self._h))
 
     def image(self):
         out = np.empty(RENDERING_SIZE, np.float32, order="F")

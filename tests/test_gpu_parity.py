@@ -159,6 +159,30 @@ def test_chain_bit_exact(synth, Fs, mode, frames, alpha):
     ch.close()
 
 
+def test_chain_overlap_modes_agree(synth):
+    # three buffers through the two-stream pipeline and through the serial path: identical results
+    Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)
+    S = orc.frame_samples(Fs, fv)
+    n = 5 * S + 3
+    outs = []
+    for overlap in (True, False):
+        ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=0.1, max_samples=n, overlap=overlap)
+        offs = []
+        for b in range(3):
+            ch.push(synth.make_iq(n, Fs, x_t, y_t, fv, seed=40 + b, t0=b * n))
+            offs.append(ch.offsets() if b == 2 else None)
+        outs.append((ch.image(), offs[2]))
+        ch.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1][0], outs[1][1][0]) and np.array_equal(outs[0][1][1], outs[1][1][1])
+    so = orc.SyncXY()
+    acc = np.zeros((600, 800), np.float32)
+    for b in range(3):
+        acc, _, sy, sx = orc.chain_buffer(synth.make_iq(n, Fs, x_t, y_t, fv, seed=40 + b, t0=b * n), Fs, x_t, y_t, fv, 0.1, so, acc,
+                                          publish=False)
+    assert np.array_equal(outs[0][0], acc) and np.array_equal(outs[0][1][0], sy) and np.array_equal(outs[0][1][1], sx)
+
+
 def test_chain_device_pointer_unaligned_and_reconfigure(synth):
     import torch
     Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)
