@@ -48,6 +48,7 @@ SIGNATURES = {
     "tsdr_chain_reset": (C.c_int, [_vp]),
     "tsdr_chain_push_host": (C.c_int, [_vp, _vp, C.c_size_t, _ip]),
     "tsdr_chain_push_device": (C.c_int, [_vp, _vp, C.c_size_t, _ip]),
+    "tsdr_chain_prime_host": (C.c_int, [_vp, _vp, C.c_size_t]),
     "tsdr_chain_sync": (C.c_int, [_vp]),
     "tsdr_chain_flush": (C.c_int, [_vp]),
     "tsdr_chain_read_image": (C.c_int, [_vp, _vp]),

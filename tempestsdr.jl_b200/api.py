@@ -253,6 +253,12 @@ class Chain:
         self._keep = z  # the copy is asynchronous: keep the buffer alive until the next sync
         return nf.value
 
+    def prime(self, iq):
+        """advance only the SyncXY state with these frames (halo frame of a sharded integration)"""
+        z, n = _iq(iq)
+        check(_lib.load().tsdr_chain_prime_host(self._h, _ptr(z), n))
+        self._keep = z
+
     def push_host_ptr(self, ptr, n):
         nf = C.c_int(0)
         check(_lib.load().tsdr_chain_push_host(self._h, C.c_void_p(ptr), int(n), C.byref(nf)))

@@ -284,3 +284,98 @@ def test_extract_configuration_recovers_refresh(synth):
     assert y_hat == 1 / (fv_hat * (m / Fs))
     name = list(tsdr.find_closest_configuration(y_hat, fv_hat))[0]
     assert tsdr.allVideoConfigurations[name].refresh == 60.0
+
+
+# ------------------------------------------------------------- sharded integration (cfg 5 logic)
+def test_block_integration_with_halo_matches_sequential(synth):
+    """two 'ranks' on one GPU: contiguous blocks of frames, each chain primed with the halo frame;
+    offsets must equal the sequential run exactly, the recombined EMA within Float32 rounding order."""
+    from tempestsdr_b200 import parallel
+    Fs, (x_t, y_t, fv), alpha = 2.0e6, (1056, 628, 60.0), 0.2
+    S = orc.frame_samples(Fs, fv)
+    N = 7
+    iq = synth.make_iq(N * S, Fs, x_t, y_t, fv, seed=77)
+    so = orc.SyncXY()
+    ref, _, sy_ref, sx_ref = orc.chain_buffer(iq, Fs, x_t, y_t, fv, alpha, so, np.zeros((600, 800), np.float32), publish=False)
+    total = np.zeros((600, 800), np.float64)
+    sy_all, sx_all = [], []
+    for rank in range(2):
+        k0, k1 = parallel.shard_contiguous(N, 2, rank)
+        ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=alpha, max_samples=(k1 - k0) * S)
+        if k0 > 0:
+            ch.prime(iq[(k0 - 1) * S:k0 * S])
+        assert ch.push(iq[k0 * S:k1 * S]) == k1 - k0
+        sy, sx = ch.offsets()
+        sy_all += list(sy); sx_all += list(sx)
+        total += ch.image().astype(np.float64) * parallel.ema_tail_weight(alpha, N - k1)
+        ch.close()
+    assert sy_all == list(sy_ref) and sx_all == list(sx_ref)
+    np.testing.assert_allclose(total, ref, rtol=2e-6, atol=1e-7)
+
+
+def _nccl_worker(rank, world, port, iq, Fs, mode, alpha, N, out_path):
+    import os
+    import torch
+    import torch.distributed as dist
+    from tempestsdr_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    x_t, y_t, fv = mode
+    S = orc.frame_samples(Fs, fv)
+    k0, k1 = parallel.shard_contiguous(N, world, rank)
+    img, ch = parallel.integrate_frames_sharded(
+        lambda: tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=alpha, max_samples=(k1 - k0) * S, device=rank),
+        lambda a, b: iq[a * S:b * S], N, alpha, rank, world)
+    if rank == 0:
+        np.save(out_path, img.cpu().numpy())
+    ch.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_nccl_allreduce_of_partial_frames(synth, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    Fs, mode, alpha, N = 2.0e6, (1056, 628, 60.0), 0.2, 6
+    S = orc.frame_samples(Fs, mode[2])
+    iq = synth.make_iq(N * S, Fs, *mode, seed=78)
+    ref, *_ = orc.chain_buffer(iq, Fs, *mode, alpha, orc.SyncXY(), np.zeros((600, 800), np.float32), publish=False)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "img.npy")
+    mp.spawn(_nccl_worker, args=(2, port, iq, Fs, mode, alpha, N, out), nprocs=2, join=True)
+    np.testing.assert_allclose(np.load(out), ref, rtol=2e-6, atol=1e-7)
+
+
+def test_gpu_matches_committed_goldens():
+    import hashlib
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    G = np.load(os.path.join(here, "golden", "golden_v1.npz"))
+    sha = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, np.float32).tobytes()).digest(), np.uint8)
+    assert np.array_equal(tsdr.amDemod(G["demod_in"]), G["amDemod"])
+    assert np.array_equal(tsdr.invert_amDemod(G["demod_in"]), G["invert_amDemod"])
+    assert np.array_equal(tsdr.abs2(G["demod_in"]), G["abs2"])
+    assert np.array_equal(tsdr.sig_to_image(G["resize_in"], 45, 52), G["sig_to_image_up"])
+    assert np.array_equal(tsdr.sig_to_image(G["resize_in"], 20, 33), G["sig_to_image_down"])
+    assert np.array_equal(sha(tsdr.downgradeImage(G["downgrade_in"])), G["downgrade_small_sha256"])
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    c = mg.CHAIN_CASE
+    iq = mg.chain_inputs()
+    ch = tsdr.Chain(c["Fs"], tsdr.VideoMode(c["x_t"], c["y_t"], c["fv"]), alpha=c["alpha"], max_samples=iq.size)
+    assert ch.push(iq) == c["frames"]
+    sy, sx = ch.offsets()
+    assert np.array_equal(sy, G["chain_sy"]) and np.array_equal(sx, G["chain_sx"])
+    assert np.array_equal(sha(ch.image()), G["chain_image_sha256"])
+    ch.close()
+    got, _ = tsdr.calculate_autocorrelation(G["autocorr_in"], 6000.0, 0, 0.5)
+    assert np.max(np.abs(got - G["autocorr_db"])) <= 1e-2

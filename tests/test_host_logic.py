@@ -1,0 +1,43 @@
+"""CPU tests of the host-side mirror: VideoMode table and lookups (the reference keeps these in
+Julia host code, src/VideoConfigurations.jl), zoom_autocorr slicing, lag/line conversions."""
+import numpy as np
+
+import tempestsdr_b200 as tsdr
+
+
+def test_video_mode_table_like_reference_runtests():
+    # test/runtests.jl:29-51: a Dict{String,VideoMode} with more than 10 entries, every entry findable
+    d = tsdr.allVideoConfigurations
+    assert isinstance(d, dict) and len(d) == 80 and len(d) > 10
+    assert all(isinstance(k, str) and isinstance(v, tsdr.VideoMode) for k, v in d.items())
+    for name, cfg in d.items():
+        found = tsdr.find_closest_configuration(cfg.height, cfg.refresh)
+        assert any(v == cfg for v in found.values()), name
+        assert tsdr.find_configuration(cfg) is not None
+    assert sorted(set(v.refresh for v in d.values())) == [25, 30, 43, 56, 60, 65, 70, 72, 75, 76, 85, 100, 120]
+
+
+def test_find_closest_follows_the_code_not_the_docstring():
+    # src/VideoConfigurations.jl:114-115 claims "1024x600 @ 60 Hz"; the code picks the 60 Hz entry whose HEIGHT is nearest
+    got = tsdr.find_closest_configuration(1280, 60)
+    assert list(got) == ["1600x1200 @ 60Hz"] and tsdr.dict2video(got) == tsdr.VideoMode(2160, 1250, 60)
+    assert tsdr.find_configuration(tsdr.VideoMode(2592, 1242, 60)) == "1920x1200 @ 60Hz"
+    assert tsdr.find_configuration(tsdr.VideoMode(1, 2, 3)) is None
+    assert list(tsdr.find_closest_configuration(1589, 60.14)) == ["2048x1536 @ 60Hz"]  # docs/src/gui.md:29 known answer
+    both = tsdr.find_closest_configuration(795, 60)  # two 60 Hz modes share height 795: both are returned
+    assert sorted(both) == ["1280x768 @ 60 Hz", "1368x768 @ 60 Hz"]
+
+
+def test_video_mode_means_total_raster():
+    m = tsdr.allVideoConfigurations["1920x1080 @ 60Hz"]
+    assert (m.width, m.height, m.refresh) == (2576, 1125, 60.0)
+    assert tsdr.getImageDuration(m, 20e6) == 333333
+
+
+def test_zoom_and_conversions():
+    g = np.arange(1, 2_000_001, dtype=np.float32)
+    rates, sl = tsdr.zoom_autocorr(g, 20e6, rate_min=50, rate_max=90)
+    assert sl[0] == 222222 and sl[-1] == 400000 and rates.size == sl.size
+    assert tsdr.delay2yt(1 / (60 * 1125), 60) == 1125 and tsdr.yt2index(1125, 20e6, 60) == 296
+    assert abs(tsdr.yt2delay(1125, 60) - 1 / 67500) < 1e-18
+    assert tsdr.RENDERING_SIZE == (600, 800)
