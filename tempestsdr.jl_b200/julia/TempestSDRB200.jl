@@ -1,0 +1,183 @@
+# TempestSDRB200.jl -- ccall binding of libtempest_b200.so for TempestSDR.jl hosts.
+#
+# Julia is not installed in the build image, so this file has never been executed there; it is
+# kept mechanical and mirrors, call for call, the ctypes binding in ../api.py that the GPU
+# parity tests exercise.  Usage from the reference (see INTEGRATION.md):
+#
+#     include("TempestSDRB200.jl"); using .TempestSDRB200
+#     TempestSDRB200.use!(TempestSDR)      # rebinds amDemod, sig_to_image, ... to the GPU versions
+#
+# Every function keeps the reference signature (src/TempestSDR.jl:21-47 exports).  Matrices are
+# plain column-major Julia Arrays, ComplexF32 vectors are passed as they are (interleaved re, im).
+module TempestSDRB200
+
+export amDemod, invert_amDemod, sig_to_image, downgradeImage, naiveResampler,
+       calculate_autocorrelation, zoom_autocorr, SyncXY, vsync, Chain, push!, image, offsets
+
+const LIB = get(ENV, "TEMPEST_B200_LIB", joinpath(@__DIR__, "..", "libtempest_b200.so"))
+const RENDERING_SIZE = (600, 800)                      # src/GUI.jl:10
+
+struct TempestB200Error <: Exception
+    status::Cint
+    msg::String
+end
+Base.showerror(io::IO, e::TempestB200Error) = print(io, "libtempest_b200 status $(e.status): $(e.msg)")
+
+# Non-zero status -> exception (ErrorException-like), so the reference's try/catch blocks
+# (src/GUI.jl:197-200) behave as before.  -5 is the reference's BoundsError.
+function check(status::Cint)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:tsdr_last_error_string, LIB), Cstring, ()))
+    status == -5 && throw(BoundsError())
+    throw(TempestB200Error(status, msg))
+end
+
+# ---- Demodulation.jl -----------------------------------------------------------------------
+function amDemod(sig::Array{ComplexF32})                                  # src/Demodulation.jl:26-28
+    out = Array{Float32}(undef, size(sig))
+    GC.@preserve sig out check(ccall((:tsdr_am_demod_f32, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
+                                     pointer(sig), pointer(out), length(sig)))
+    return out
+end
+
+function invert_amDemod(sig::Array{ComplexF32})                           # src/Demodulation.jl:31-35
+    out = Array{Float32}(undef, size(sig))
+    GC.@preserve sig out check(ccall((:tsdr_invert_am_demod_f32, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
+                                     pointer(sig), pointer(out), length(sig)))
+    return out
+end
+
+# ---- Resampler.jl --------------------------------------------------------------------------
+function sig_to_image(sig::AbstractVector{Float32}, y_t, x_t)              # src/Resampler.jl:117-122
+    s = sig isa Vector{Float32} ? sig : collect(sig)                       # views are copied once
+    out = Matrix{Float32}(undef, Int(y_t), Int(x_t))
+    GC.@preserve s out check(ccall((:tsdr_sig_to_image_f32, LIB), Cint,
+                                   (Ptr{Cvoid}, Csize_t, Cint, Cint, Ptr{Cvoid}),
+                                   pointer(s), length(s), y_t, x_t, pointer(out)))
+    return out
+end
+
+function downgradeImage(image::Matrix{Float32})                            # src/Resampler.jl:124-126
+    out = Matrix{Float32}(undef, RENDERING_SIZE...)
+    GC.@preserve image out check(ccall((:tsdr_downgrade_f32, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}),
+                                       pointer(image), size(image, 1), size(image, 2), pointer(out)))
+    return out
+end
+
+function naiveResampler(sigOut::Vector{Float32}, sigId::Vector{Float32}, upCoeff)   # src/Resampler.jl:103-110
+    length(sigOut) >= upCoeff * length(sigId) || throw(BoundsError(sigOut, upCoeff * length(sigId)))
+    GC.@preserve sigOut sigId check(ccall((:tsdr_naive_resampler_f32, LIB), Cint,
+                                          (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Cint),
+                                          pointer(sigOut), pointer(sigId), length(sigId), upCoeff))
+    return nothing
+end
+
+# ---- Autocorrelations.jl -------------------------------------------------------------------
+function calculate_autocorrelation(x::Vector{Float32}, Fs, minDelay, maxDelay, scale = :log)   # :23-37
+    n = Ref{Csize_t}(0)
+    check(ccall((:tsdr_autocorr_out_len, LIB), Cint, (Csize_t, Cdouble, Cdouble, Cdouble, Ptr{Csize_t}),
+                length(x), Fs, minDelay, maxDelay, n))
+    out = Vector{Float32}(undef, n[])
+    GC.@preserve x out check(ccall((:tsdr_autocorr_f32, LIB), Cint,
+                                   (Ptr{Cvoid}, Csize_t, Cdouble, Cdouble, Cdouble, Cint, Ptr{Cvoid}, Ptr{Csize_t}),
+                                   pointer(x), length(x), Fs, minDelay, maxDelay, scale == :log ? 1 : 0, pointer(out), n))
+    indexMin = 1 + Int(round(minDelay * Fs)); indexMax = Int(round(maxDelay * Fs))
+    lags = (0:(indexMax - indexMin)) * 1 / Fs
+    return out, lags
+end
+
+# zoom_autocorr is index arithmetic on the host; it stays as in src/Autocorrelations.jl:42-53.
+function zoom_autocorr(Γ, Fs; rate_min = 20, rate_max = 100)
+    N = length(Γ)
+    pos_rate_min = min(Int(round(1 / rate_max * Fs)), N)
+    pos_rate_max = min(Int(round(1 / rate_min * Fs)), N)
+    return 1 ./ ((pos_rate_min:pos_rate_max) ./ Fs), Γ[pos_rate_min:pos_rate_max]
+end
+
+# ---- FrameSynchronisation.jl ---------------------------------------------------------------
+mutable struct SyncXY{T}                                                   # :25-48 ; state lives on the GPU
+    handle::Ptr{Cvoid}
+    n_y::Int
+    n_x::Int
+    function SyncXY(image::Matrix{T}) where T
+        T === Float32 || error("libtempest_b200 implements SyncXY for Float32 images")
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:tsdr_sync_create, LIB), Cint, (Cint, Cint, Ptr{Ptr{Cvoid}}), size(image, 1), size(image, 2), h))
+        s = new{T}(h[], size(image, 1), size(image, 2))
+        finalizer(x -> ccall((:tsdr_sync_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), s)
+        return s
+    end
+end
+
+function vsync(image::AbstractMatrix{Float32}, sync::SyncXY{Float32})      # :56-79 -> (s_y, s_x), 1-based
+    img = image isa Matrix{Float32} ? image : collect(image)
+    sy = Ref{Cint}(0); sx = Ref{Cint}(0)
+    GC.@preserve img check(ccall((:tsdr_vsync_f32, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}),
+                                 sync.handle, pointer(img), sy, sx))
+    return (Int(sy[]), Int(sx[]))
+end
+
+# β_x / β_y of the Julia struct, copied out on demand (column-major, (1+wmax-wmin) x n)
+function betas(sync::SyncXY{Float32})
+    b = Ref{Cint}.((0, 0, 0, 0))
+    check(ccall((:tsdr_sync_bounds, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), sync.handle, b...))
+    wmin_y, wmax_y, wmin_x, wmax_x = getindex.(b)
+    βx = Matrix{Float32}(undef, 1 + wmax_x - wmin_x, sync.n_x); βy = Matrix{Float32}(undef, 1 + wmax_y - wmin_y, sync.n_y)
+    GC.@preserve βx βy check(ccall((:tsdr_sync_get_beta, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                                   sync.handle, pointer(βx), pointer(βy)))
+    return βx, βy
+end
+
+# ---- the fused loop body of coreProcessing (src/GUI.jl:163-178) ------------------------------
+mutable struct Chain
+    handle::Ptr{Cvoid}
+    function Chain(Fs, x_t, y_t, fv; alpha = 0.1f0, max_samples, device = 0, flags = 0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:tsdr_chain_create, LIB), Cint,
+                    (Ptr{Ptr{Cvoid}}, Cint, Cdouble, Cint, Cint, Cdouble, Cfloat, Csize_t, Cuint, Ptr{Cvoid}),
+                    h, device, Fs, x_t, y_t, fv, alpha, max_samples, flags, C_NULL))
+        c = new(h[])
+        finalizer(x -> ccall((:tsdr_chain_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), c)
+        return c
+    end
+end
+
+# one recv! buffer: amDemod -> sig_to_image -> downgradeImage -> vsync -> circshift -> EMA for every frame
+function Base.push!(c::Chain, sigId::Vector{ComplexF32})
+    n = Ref{Cint}(0)
+    GC.@preserve sigId begin
+        check(ccall((:tsdr_chain_push_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cint}),
+                    c.handle, pointer(sigId), length(sigId), n))
+        check(ccall((:tsdr_chain_sync, LIB), Cint, (Ptr{Cvoid},), c.handle))   # sigId may be reused after return
+    end
+    return Int(n[])
+end
+
+function image(c::Chain)                                                   # imageOut, 600 x 800
+    out = Matrix{Float32}(undef, RENDERING_SIZE...)
+    GC.@preserve out check(ccall((:tsdr_chain_read_image, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c.handle, pointer(out)))
+    return out
+end
+
+function offsets(c::Chain, maxframes = 4096)
+    sy = Vector{Cint}(undef, maxframes); sx = Vector{Cint}(undef, maxframes); n = Ref{Cint}(0)
+    GC.@preserve sy sx check(ccall((:tsdr_chain_read_offsets, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Cint, Ptr{Cint}),
+                                   c.handle, pointer(sy), pointer(sx), maxframes, n))
+    k = min(Int(n[]), maxframes)
+    return Int.(sy[1:k]), Int.(sx[1:k])
+end
+
+configure!(c::Chain, Fs, x_t, y_t, fv) = check(ccall((:tsdr_chain_configure, LIB), Cint,
+                                                     (Ptr{Cvoid}, Cdouble, Cint, Cint, Cdouble), c.handle, Fs, x_t, y_t, fv))
+set_alpha!(c::Chain, α) = check(ccall((:tsdr_chain_set_alpha, LIB), Cint, (Ptr{Cvoid}, Cfloat), c.handle, α))
+
+# Rebind the reference module's DSP functions to the GPU versions (same names, same signatures).
+function use!(ref::Module)
+    for f in (:amDemod, :invert_amDemod, :sig_to_image, :downgradeImage, :naiveResampler,
+              :calculate_autocorrelation, :zoom_autocorr, :vsync)
+        Core.eval(ref, :($f(args...; kw...) = $(getfield(TempestSDRB200, f))(args...; kw...)))
+    end
+    return nothing
+end
+
+end # module
