@@ -164,7 +164,11 @@ def filt5(h, x):
 def fill_beta(c, wmin, wmax):  # src/FrameSynchronisation.jl:94-112 -> (nw, n)
     c = np.asarray(c, np.float32)
     n = c.size
-    Sigma = seq_sum(c)
+    # Sigma = sum(c): fixed to a 32-lane SIMD-shaped order (see tsdr_oracle.c:orc_fill_beta)
+    lanes = [seq_sum(c[l::32]) for l in range(min(32, n))]
+    Sigma = lanes[0]
+    for v in lanes[1:]:
+        Sigma = np.float32(Sigma + v)
     ctr = np.arange(n)  # 0-based centres
     acc = np.zeros(n, np.float32)
     for k in range(-(wmin - 1), wmin):

@@ -315,9 +315,15 @@ static inline int orc_mod_index(int k, int n) { /* modIndex :120-122, returns 0-
 }
 
 void orc_fill_beta(float* beta, const float* c, int n, int wmin, int wmax) { /* :94-112 */
-    /* Sigma = sum(c_v): fixed to sequential order (Base uses a @simd loop below 1024 elements) */
-    float Sigma = c[0];
-    for (int i = 1; i < n; ++i) Sigma = Sigma + c[i];
+    /* Sigma = sum(c_v): Base uses a @simd loop below 1024 elements, whose association is CPU
+     * dependent.  FIXED here to the shape of a 32-lane SIMD reduction: lane l adds elements
+     * l, l+32, l+64, ... in order, then the lane sums are added in lane order. */
+    float Sigma = 0.0f;
+    for (int l = 0; l < 32 && l < n; ++l) {
+        float part = c[l];
+        for (int i = l + 32; i < n; i += 32) part = part + c[i];
+        Sigma = (l == 0) ? part : Sigma + part;
+    }
     const int nw = 1 + wmax - wmin;
     for (int ctr = 1; ctr <= n; ++ctr) {
         /* averagePixel(c_v, c, wmin-1, n): accum starts as Int 0 -> first add is exact */

@@ -447,8 +447,8 @@ static const unsigned long long kBestInit = 0x00000000ffffffffull;  // beta = 0 
 
 static int launch_sync_stage(const float* frames, int n_frames, float* c_v, float* c_h, const SyncParams& sp,
                              cudaStream_t st) {
-    k_project<<<dim3(kBands, n_frames), kProjThreads, kProjSmem, st>>>(frames, c_v, c_h);
-    k_fir_sigma<<<dim3(n_frames, 2), kFirThreads, 0, st>>>(sp);
+    (void)c_v; (void)c_h;
+    k_project<<<dim3(kBands, n_frames), kProjThreads, kProjSmem, st>>>(frames, sp);
     k_beta<<<dim3(n_frames, kBetaCtasX + kBetaCtasY), kBetaThreads, 0, st>>>(sp);
     return TSDR_OK;
 }
@@ -462,7 +462,7 @@ struct tsdr_sync {
     float* d_img_cm;   // staging, column-major
     float* d_img;      // scan order
     float* d_cv; float* d_ch;
-    float* d_cfv; float* d_cfh; float* d_sigma;
+    float* d_cfv; float* d_cfh; float* d_sigma; unsigned int* d_tickets;
     float* d_beta_x; float* d_beta_y;
     unsigned long long* d_best;  // [2][2]
     int* d_off;                  // [2]
@@ -494,6 +494,8 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cfv, n_x * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cfh, n_y * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_sigma, 2 * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_tickets, 4);
+    if (e == cudaSuccess) e = cudaMemset(s->d_tickets, 0, 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_beta_x, nbx * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_beta_y, nby * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_best, 4 * 8);
@@ -504,7 +506,7 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     if (e == cudaSuccess) e = cudaMemcpy(s->d_best, init, sizeof(init), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { tsdr_sync_destroy(s); return cuda_fail(e, "tsdr_sync_create", __FILE__, __LINE__); }
     sp.colpart = s->d_cv; sp.c_h = s->d_ch; sp.best = s->d_best; sp.beta_x = s->d_beta_x; sp.beta_y = s->d_beta_y;
-    sp.cf_v = s->d_cfv; sp.cf_h = s->d_cfh; sp.sigma = s->d_sigma;
+    sp.cf_v = s->d_cfv; sp.cf_h = s->d_cfh; sp.sigma = s->d_sigma; sp.tickets = s->d_tickets;
     *out = s;
     return TSDR_OK;
 }
@@ -547,7 +549,7 @@ int tsdr_sync_destroy(tsdr_sync* s) {
     if (!s) return TSDR_OK;
     cudaSetDevice(s->device);
     cudaFree(s->d_img_cm); cudaFree(s->d_img); cudaFree(s->d_cv); cudaFree(s->d_ch);
-    cudaFree(s->d_cfv); cudaFree(s->d_cfh); cudaFree(s->d_sigma);
+    cudaFree(s->d_cfv); cudaFree(s->d_cfh); cudaFree(s->d_sigma); cudaFree(s->d_tickets);
     cudaFree(s->d_beta_x); cudaFree(s->d_beta_y); cudaFree(s->d_best); cudaFree(s->d_off);
     delete s;
     return TSDR_OK;
@@ -583,7 +585,7 @@ struct tsdr_chain {
     float* d_acc;       // imageOut, scan order
     float* d_tmp;       // 600x800 transpose target
     float* d_cv; float* d_ch;
-    float* d_cfv; float* d_cfh; float* d_sigma;
+    float* d_cfv; float* d_cfh; float* d_sigma; unsigned int* d_tickets;
     unsigned long long* d_best;
     int* d_sy; int* d_sx;
     int* d_fy; double* d_dy; double* d_kd; double* d_dx; int* d_win_lo; int* d_win_len;
@@ -614,6 +616,7 @@ static void chain_free_frames(tsdr_chain* c) {
     cudaFree(c->d_cfv); c->d_cfv = nullptr;
     cudaFree(c->d_cfh); c->d_cfh = nullptr;
     cudaFree(c->d_sigma); c->d_sigma = nullptr;
+    cudaFree(c->d_tickets); c->d_tickets = nullptr;
     cudaFree(c->d_best); c->d_best = nullptr;
     cudaFree(c->d_sy); c->d_sy = nullptr;
     cudaFree(c->d_sx); c->d_sx = nullptr;
@@ -676,6 +679,8 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         TSDR_CUDA(cudaMalloc(&c->d_cfv, (size_t)max_frames * kRenderW * 4));
         TSDR_CUDA(cudaMalloc(&c->d_cfh, (size_t)max_frames * kRenderH * 4));
         TSDR_CUDA(cudaMalloc(&c->d_sigma, (size_t)max_frames * 2 * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_tickets, (size_t)max_frames * 4));
+        TSDR_CUDA(cudaMemsetAsync(c->d_tickets, 0, (size_t)max_frames * 4, c->stream));
         TSDR_CUDA(cudaMalloc(&c->d_best, (size_t)(max_frames + 1) * 2 * 8));
         TSDR_CUDA(cudaMalloc(&c->d_sy, (size_t)max_frames * 4));
         TSDR_CUDA(cudaMalloc(&c->d_sx, (size_t)max_frames * 4));
@@ -720,7 +725,7 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     sp.wmin_y = (int)ceil(1.0 / 100.0 * (double)kRenderH); sp.wmax_y = (int)floor((double)kRenderH / 4.0);
     sp.wmin_x = (int)ceil(5.0 / 100.0 * (double)kRenderW); sp.wmax_x = (int)floor((double)kRenderW / 4.0);
     sp.colpart = c->d_cv; sp.c_h = c->d_ch; sp.best = c->d_best; sp.beta_x = nullptr; sp.beta_y = nullptr;
-    sp.cf_v = c->d_cfv; sp.cf_h = c->d_cfh; sp.sigma = c->d_sigma;
+    sp.cf_v = c->d_cfv; sp.cf_h = c->d_cfh; sp.sigma = c->d_sigma; sp.tickets = c->d_tickets;
     return TSDR_OK;
 }
 
@@ -771,7 +776,7 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
         c->aux_busy = true;
     }
     const int align = !(c->flags & TSDR_CHAIN_NO_ALIGN);
-    if (align) { launch_sync_stage(rp.frames, nb, c->d_cv, c->d_ch, c->sp, st2); c->launches += 3; }
+    if (align) { launch_sync_stage(rp.frames, nb, c->d_cv, c->d_ch, c->sp, st2); c->launches += 2; }
     mark(st2);
     AccumParams ap;
     ap.frames = rp.frames; ap.best = c->d_best; ap.acc = c->d_acc;
