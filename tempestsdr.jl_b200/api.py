@@ -354,7 +354,7 @@ class AutocorrPlan:
         return v.value
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "load", None):
             _lib.load().tsdr_autocorr_plan_destroy(self._h)
             self._h = None
 

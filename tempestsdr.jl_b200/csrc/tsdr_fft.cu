@@ -357,6 +357,8 @@ __global__ void __launch_bounds__(256) k_fold_lags(const float* __restrict__ lin
 
 }  // namespace tsdr
 
+#include "tsdr_fft_fast.cuh"
+
 using namespace tsdr;
 
 struct tsdr_autocorr_plan {
@@ -368,6 +370,8 @@ struct tsdr_autocorr_plan {
     bool fold;
     FftParams fp;
     size_t smem_cols, smem_mid;
+    bool has_fast;
+    FastKernels fast;
     uint64_t launches;
     void* d_tables;  // one allocation for every table
     float2* d_T; float2* d_U;
@@ -483,6 +487,18 @@ int tsdr_autocorr_plan_create(tsdr_autocorr_plan** out, int device, size_t n, vo
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cols);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ifft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cols);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fft_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_mid);
+    {
+        int loga = 0, logb = 0;
+        while ((1 << loga) < A) ++loga;
+        while ((1 << logb) < B) ++logb;
+        p->has_fast = find_fast(loga, logb, &p->fast);
+        if (p->has_fast && e == cudaSuccess) {
+            e = cudaFuncSetAttribute(p->fast.cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast.smem_cols);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->fast.cols_padded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast.smem_cols);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->fast.icols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast.smem_cols);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->fast.mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast.smem_mid);
+        }
+    }
     if (e != cudaSuccess) rc = cuda_fail(e, "tsdr_autocorr_plan_create", __FILE__, __LINE__);
     if (rc != TSDR_OK) { tsdr_autocorr_plan_destroy(p); return rc; }
     *out = p;
@@ -501,9 +517,17 @@ int tsdr_autocorr_plan_exec(tsdr_autocorr_plan* p, const float* x_dev, size_t in
     if (p->fold) { fp.out = p->d_lin; fp.m_lo = 0; fp.m_hi = (int64_t)p->n; fp.raw = 1; }
     else { fp.out = out_dev; fp.m_lo = (int64_t)index_min - 1; fp.m_hi = (int64_t)index_max - 1; fp.raw = 0; }
     cudaStream_t st = p->stream;
-    k_fft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
-    k_fft_mid<<<fp.A / 2 + 1, kFftThreads, p->smem_mid, st>>>(fp);
-    k_ifft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
+    if (p->has_fast && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) {
+        const int grid_cols = fp.B >> p->fast.logc;
+        if (p->n == p->N) p->fast.cols<<<grid_cols, kFastThreads, p->fast.smem_cols, st>>>(fp);
+        else p->fast.cols_padded<<<grid_cols, kFastThreads, p->fast.smem_cols, st>>>(fp);
+        p->fast.mid<<<fp.A / 2 + 1, kFastThreads, p->fast.smem_mid, st>>>(fp);
+        p->fast.icols<<<grid_cols, kFastThreads, p->fast.smem_cols, st>>>(fp);
+    } else {
+        k_fft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
+        k_fft_mid<<<fp.A / 2 + 1, kFftThreads, p->smem_mid, st>>>(fp);
+        k_ifft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
+    }
     p->launches += 3;
     if (p->fold) {
         const int64_t count = (int64_t)(index_max - index_min + 1);

@@ -1,0 +1,282 @@
+// tsdr_fft_fast.cuh -- compile-time specialised versions of the three autocorrelation kernels.
+// Included by tsdr_fft.cu after the generic definitions (same algorithm, same layouts of T/U,
+// same digit-reversed ordering: the tables revA/posA/revB/posB are shared).  Everything that
+// the generic kernels compute with run-time divisions is a shift or a constant here, stage
+// loops are fully unrolled, and each CTA has 256 threads doing two radix-16 butterflies per
+// stage so that three CTAs (<= 70 KB of shared memory, ~80 registers) share an SM.
+#pragma once
+
+namespace tsdr {
+
+constexpr int kFastThreads = 256;
+
+// radix plan of a 2^LOGLEN transform: first stage 2^(LOGLEN % 4) when non-zero, then radix 16
+template <int LOGLEN> struct CtPlan {
+    static constexpr int rem = LOGLEN % 4;
+    static constexpr int nst = LOGLEN / 4 + (rem ? 1 : 0);
+    __host__ __device__ static constexpr int logr(int i) { return (rem && i == 0) ? rem : 4; }
+    __host__ __device__ static constexpr int loglcur(int i) {  // log2 of the sub-transform length at stage i
+        int l = LOGLEN;
+        for (int j = 0; j < i; ++j) l -= logr(j);
+        return l;
+    }
+};
+
+struct RowLayoutCt {  // contiguous transform, one pad element per 16
+    int row_stride;
+    __device__ __forceinline__ int operator()(int b, int i) const { return b * row_stride + i + (i >> 4); }
+};
+template <int LOGC> struct ColLayoutCt {  // 2^LOGC interleaved transforms, 4 pad elements per 64
+    __device__ __forceinline__ int operator()(int b, int i) const { const int e = (i << LOGC) + b; return e + ((e >> 6) << 2); }
+};
+template <int LOGC> __host__ __device__ constexpr int col_padded_ct(int total) { return total + ((total >> 6) << 2) + 4; }
+
+template <int LOGLEN, int LOGR, int LOGLCUR, int DIR, bool COLFAST, int LOGNB, class Layout>
+__device__ __forceinline__ void stage_ct(float2* s, const Layout lay, const float2* __restrict__ tw, int tid) {
+    constexpr int R = 1 << LOGR;
+    constexpr int LOGSUB = LOGLCUR - LOGR;
+    constexpr int LOGPER = LOGLEN - LOGR;
+    constexpr int TOTAL = 1 << (LOGNB + LOGPER);
+    constexpr int TWSHIFT = LOGLEN - LOGLCUR;
+#pragma unroll 1
+    for (int e0 = 0; e0 < TOTAL; e0 += kFastThreads) {
+        const int e = e0 + tid;
+        if (TOTAL < kFastThreads && e >= TOTAL) break;
+        int b, w;
+        if (COLFAST) { b = e & ((1 << LOGNB) - 1); w = e >> LOGNB; }
+        else { b = e >> LOGPER; w = e & ((1 << LOGPER) - 1); }
+        const int blk = w >> LOGSUB, u = w & ((1 << LOGSUB) - 1);
+        const int base = (blk << LOGLCUR) + u;
+        float2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = s[lay(b, base + (q << LOGSUB))];
+        if (DIR < 0 && LOGSUB > 0) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], cconj(__ldg(tw + ((u * q) << TWSHIFT))));
+        }
+        dft<R, DIR>(x);
+        if (DIR > 0 && LOGSUB > 0) {
+#pragma unroll
+            for (int p = 1; p < R; ++p) x[p] = cmul(x[p], __ldg(tw + ((u * p) << TWSHIFT)));
+        }
+#pragma unroll
+        for (int p = 0; p < R; ++p) s[lay(b, base + (p << LOGSUB))] = x[p];
+    }
+}
+
+template <int LOGLEN, int STAGE, bool COLFAST, int LOGNB, class Layout>
+__device__ __forceinline__ void fft_fwd_ct(float2* s, const Layout lay, const float2* __restrict__ tw, int tid) {
+    if constexpr (STAGE < CtPlan<LOGLEN>::nst) {
+        stage_ct<LOGLEN, CtPlan<LOGLEN>::logr(STAGE), CtPlan<LOGLEN>::loglcur(STAGE), +1, COLFAST, LOGNB>(s, lay, tw, tid);
+        __syncthreads();
+        fft_fwd_ct<LOGLEN, STAGE + 1, COLFAST, LOGNB>(s, lay, tw, tid);
+    }
+}
+template <int LOGLEN, int STAGE, bool COLFAST, int LOGNB, class Layout>
+__device__ __forceinline__ void fft_inv_ct(float2* s, const Layout lay, const float2* __restrict__ tw, int tid) {
+    if constexpr (STAGE >= 0) {
+        stage_ct<LOGLEN, CtPlan<LOGLEN>::logr(STAGE), CtPlan<LOGLEN>::loglcur(STAGE), -1, COLFAST, LOGNB>(s, lay, tw, tid);
+        __syncthreads();
+        fft_inv_ct<LOGLEN, STAGE - 1, COLFAST, LOGNB>(s, lay, tw, tid);
+    }
+}
+
+// ---------------------------------------------------------------- columns, forward --
+template <int LOGA, int LOGB, int LOGC, bool PADDED>
+__global__ void __launch_bounds__(kFastThreads, 3) k_fft_cols_ct(FftParams p) {
+    extern __shared__ float2 sm[];
+    constexpr int A = 1 << LOGA, C = 1 << LOGC;
+    const int tid = threadIdx.x;
+    const int j2_0 = blockIdx.x << LOGC;
+    const ColLayoutCt<LOGC> lay;
+    // 16-byte loads: two adjacent columns per thread
+    constexpr int HALF = C / 2;
+#pragma unroll 4
+    for (int e = tid; e < A * HALF; e += kFastThreads) {
+        const int j1 = e / HALF, c2 = (e - j1 * HALF) * 2;
+        const int64_t j = ((int64_t)j1 << LOGB) + j2_0 + c2;
+        float4 v;
+        if (!PADDED || 2 * j + 3 < p.n_valid) v = __ldg(reinterpret_cast<const float4*>(p.x) + (j >> 1));
+        else {
+            v.x = 2 * j < p.n_valid ? __ldg(p.x + 2 * j) : 0.f;
+            v.y = 2 * j + 1 < p.n_valid ? __ldg(p.x + 2 * j + 1) : 0.f;
+            v.z = 2 * j + 2 < p.n_valid ? __ldg(p.x + 2 * j + 2) : 0.f;
+            v.w = 0.f;
+        }
+        sm[lay(c2, j1)] = make_float2(v.x, v.y);
+        sm[lay(c2 + 1, j1)] = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+    fft_fwd_ct<LOGA, 0, true, LOGC>(sm, lay, p.twA, tid);
+#pragma unroll 4
+    for (int e = tid; e < A * HALF; e += kFastThreads) {
+        const int row = e / HALF, c2 = (e - row * HALF) * 2;
+        const int k1 = __ldg(p.revA + row);
+        const int j2 = j2_0 + c2;
+        const float2 a = cmul(sm[lay(c2, row)], twiddle_n(p, 2 * (int64_t)j2 * k1));          // W_M^(j2 k1) = W_N^(2 j2 k1)
+        const float2 b = cmul(sm[lay(c2 + 1, row)], twiddle_n(p, 2 * (int64_t)(j2 + 1) * k1));
+        reinterpret_cast<float4*>(p.T)[(((int64_t)row << LOGB) + j2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+
+// ------------------------------------------------------------------------- middle --
+__device__ __forceinline__ void mid_pair(const FftParams& p, float2& zk_io, float2& zm_io, int64_t k, float sc) {
+    const float2 zk = zk_io, zm = zm_io;
+    const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+    const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+    const float2 w = twiddle_n(p, k);
+    const float2 wO = cmul(w, O);
+    const float2 xp = cadd(E, wO), xm = csub(E, wO);
+    const float P = fmaf(xp.x, xp.x, xp.y * xp.y), Pm = fmaf(xm.x, xm.x, xm.y * xm.y);
+    const float S = (P + Pm) * sc, D = (P - Pm) * sc;
+    zk_io = make_float2(S + w.y * D, w.x * D);   // Y[k]   = S + i conj(w) D
+    zm_io = make_float2(S - w.y * D, w.x * D);   // Y[M-k] = S + i w D
+}
+
+template <int LOGA, int LOGB, int LOGNB>
+__device__ __forceinline__ void mid_body(const FftParams& p, float2* sm, int k1a, int k1b, int tid) {
+    constexpr int A = 1 << LOGA, B = 1 << LOGB, NR = 1 << LOGNB;
+    const int rowa = __ldg(p.posA + k1a), rowb = __ldg(p.posA + k1b);
+    const RowLayoutCt lay{B + (B >> 4) + 1};
+    for (int e = tid; e < NR * (B / 2); e += kFastThreads) {
+        const int r = e >> (LOGB - 1), i2 = (e & (B / 2 - 1)) * 2;
+        const float4 v = reinterpret_cast<const float4*>(p.T)[((((int64_t)(r == 0 ? rowa : rowb)) << LOGB) + i2) >> 1];
+        sm[lay(r, i2)] = make_float2(v.x, v.y);
+        sm[lay(r, i2 + 1)] = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+    fft_fwd_ct<LOGB, 0, false, LOGNB>(sm, lay, p.twB, tid);
+    const float sc = 0.5f * p.inv_scale;
+    if (NR == 2) {
+        for (int pos = tid; pos < B; pos += kFastThreads) {
+            const int k2 = __ldg(p.revB + pos);
+            const int pos2 = __ldg(p.posB + (B - 1 - k2));
+            mid_pair(p, sm[lay(0, pos)], sm[lay(1, pos2)], (int64_t)k1a + ((int64_t)k2 << LOGA), sc);
+        }
+    } else if (k1a == 0) {
+        for (int k2 = tid; k2 <= B / 2; k2 += kFastThreads) {
+            const int pos = __ldg(p.posB + k2);
+            if (k2 == 0) {
+                const float2 z = sm[lay(0, pos)];
+                const float P0 = (z.x + z.y) * (z.x + z.y), PM = (z.x - z.y) * (z.x - z.y);
+                sm[lay(0, pos)] = make_float2((P0 + PM) * sc, (P0 - PM) * sc);
+                continue;
+            }
+            const int pos2 = __ldg(p.posB + (B - k2));
+            float2 a = sm[lay(0, pos)], b = sm[lay(0, pos2)];
+            mid_pair(p, a, b, (int64_t)k2 << LOGA, sc);
+            sm[lay(0, pos)] = a;
+            if (pos2 != pos) sm[lay(0, pos2)] = b;
+        }
+    } else {  // k1 = A/2: k2 <-> B-1-k2
+        for (int k2 = tid; k2 < B / 2; k2 += kFastThreads) {
+            const int pos = __ldg(p.posB + k2), pos2 = __ldg(p.posB + (B - 1 - k2));
+            mid_pair(p, sm[lay(0, pos)], sm[lay(0, pos2)], (int64_t)k1a + ((int64_t)k2 << LOGA), sc);
+        }
+    }
+    __syncthreads();
+    fft_inv_ct<LOGB, CtPlan<LOGB>::nst - 1, false, LOGNB>(sm, lay, p.twB, tid);
+    for (int e = tid; e < NR * (B / 2); e += kFastThreads) {
+        const int r = e >> (LOGB - 1), j2 = (e & (B / 2 - 1)) * 2;
+        const int k1 = r == 0 ? k1a : k1b;
+        const float2 a = cmul(sm[lay(r, j2)], cconj(twiddle_n(p, 2 * (int64_t)j2 * k1)));
+        const float2 b = cmul(sm[lay(r, j2 + 1)], cconj(twiddle_n(p, 2 * (int64_t)(j2 + 1) * k1)));
+        reinterpret_cast<float4*>(p.U)[((((int64_t)(r == 0 ? rowa : rowb)) << LOGB) + j2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
+    }
+    (void)A;
+}
+
+#ifndef TSDR_FFT_MID_MINBLOCKS
+#define TSDR_FFT_MID_MINBLOCKS 2
+#endif
+template <int LOGA, int LOGB>
+__global__ void __launch_bounds__(kFastThreads, TSDR_FFT_MID_MINBLOCKS) k_fft_mid_ct(FftParams p) {
+    extern __shared__ float2 sm[];
+    constexpr int A = 1 << LOGA;
+    const int k1a = blockIdx.x;
+    const int k1b = (A - k1a) & (A - 1);
+    if (k1a == k1b) mid_body<LOGA, LOGB, 0>(p, sm, k1a, k1b, threadIdx.x);
+    else mid_body<LOGA, LOGB, 1>(p, sm, k1a, k1b, threadIdx.x);
+}
+
+// ---------------------------------------------------------------- columns, inverse --
+template <int LOGA, int LOGB, int LOGC>
+__global__ void __launch_bounds__(kFastThreads, 3) k_ifft_cols_ct(FftParams p) {
+    extern __shared__ float2 sm[];
+    constexpr int A = 1 << LOGA, C = 1 << LOGC, HALF = C / 2;
+    const int tid = threadIdx.x;
+    const int j2_0 = blockIdx.x << LOGC;
+    const ColLayoutCt<LOGC> lay;
+#pragma unroll 4
+    for (int e = tid; e < A * HALF; e += kFastThreads) {
+        const int row = e / HALF, c2 = (e - row * HALF) * 2;
+        const float4 v = reinterpret_cast<const float4*>(p.U)[(((int64_t)row << LOGB) + j2_0 + c2) >> 1];
+        sm[lay(c2, row)] = make_float2(v.x, v.y);
+        sm[lay(c2 + 1, row)] = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+    fft_inv_ct<LOGA, CtPlan<LOGA>::nst - 1, true, LOGC>(sm, lay, p.twA, tid);
+    // y[j1*B + j2] = r[2j] + i r[2j+1]; two adjacent columns = four consecutive lags
+#pragma unroll 4
+    for (int e = tid; e < A * HALF; e += kFastThreads) {
+        const int j1 = e / HALF, c2 = (e - j1 * HALF) * 2;
+        const int64_t j = ((int64_t)j1 << LOGB) + j2_0 + c2;
+        const int64_t m0 = 2 * j;
+        if (m0 > p.m_hi || m0 + 3 < p.m_lo) continue;
+        const float2 v0 = sm[lay(c2, j1)], v1 = sm[lay(c2 + 1, j1)];
+        float o[4] = {v0.x, v0.y, v1.x, v1.y};
+        if (!p.raw) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                o[t] = o[t] * o[t];  // abs2 of the (real) correlation
+                if (p.log_scale) o[t] = 10.0f * log10f(o[t]);
+            }
+        }
+        if (m0 >= p.m_lo && m0 + 3 <= p.m_hi && (((m0 - p.m_lo) & 3) == 0) && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+            *reinterpret_cast<float4*>(p.out + (m0 - p.m_lo)) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (m0 + t >= p.m_lo && m0 + t <= p.m_hi) p.out[m0 + t - p.m_lo] = o[t];
+        }
+    }
+}
+
+// --------------------------------------------------------------------- dispatch --
+struct FastKernels {
+    void (*cols)(FftParams);
+    void (*cols_padded)(FftParams);
+    void (*mid)(FftParams);
+    void (*icols)(FftParams);
+    int logc;
+    size_t smem_cols, smem_mid;
+};
+
+template <int LOGA, int LOGB, int LOGC>
+static FastKernels make_fast() {
+    FastKernels f;
+    f.cols = k_fft_cols_ct<LOGA, LOGB, LOGC, false>;
+    f.cols_padded = k_fft_cols_ct<LOGA, LOGB, LOGC, true>;
+    f.mid = k_fft_mid_ct<LOGA, LOGB>;
+    f.icols = k_ifft_cols_ct<LOGA, LOGB, LOGC>;
+    f.logc = LOGC;
+    f.smem_cols = (size_t)col_padded_ct<LOGC>((1 << LOGA) << LOGC) * sizeof(float2);
+    f.smem_mid = (size_t)2 * ((1 << LOGB) + ((1 << LOGB) >> 4) + 1) * sizeof(float2);
+    return f;
+}
+
+// shapes with a specialised build: M = 2^(LOGA+LOGB) complex points, i.e. n = 2^(LOGA+LOGB+1) samples
+static bool find_fast(int loga, int logb, FastKernels* out) {
+#define TSDR_FAST(a, b, c) if (loga == a && logb == b) { *out = make_fast<a, b, c>(); return true; }
+    TSDR_FAST(7, 12, 3)   // n = 2^20
+    TSDR_FAST(8, 12, 3)   // n = 2^21
+    TSDR_FAST(9, 12, 3)   // n = 2^22
+    TSDR_FAST(10, 12, 3)  // n = 2^23
+    TSDR_FAST(11, 12, 2)  // n = 2^24  (the benchmark size; also the GUI's 3e6 / 4e6 after zero padding: n = 2^23)
+    TSDR_FAST(11, 13, 2)  // n = 2^25
+    TSDR_FAST(12, 13, 1)  // n = 2^26
+#undef TSDR_FAST
+    return false;
+}
+
+}  // namespace tsdr
