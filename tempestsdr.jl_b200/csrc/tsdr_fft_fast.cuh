@@ -22,6 +22,31 @@ template <int LOGLEN> struct CtPlan {
     }
 };
 
+// frequency index of position `pos` after the in-place DIF (and its inverse map): the stage
+// digits are reversed.  pos = sum_i p_i * 2^(LOGLEN - sum_{j<=i} logr_j),  k = sum_i p_i * 2^(sum_{j<i} logr_j)
+template <int LOGLEN> __device__ __forceinline__ int digit_rev_ct(int pos) {
+    int k = 0, hi = LOGLEN, lo = 0;
+#pragma unroll
+    for (int i = 0; i < CtPlan<LOGLEN>::nst; ++i) {
+        const int lr = CtPlan<LOGLEN>::logr(i);
+        hi -= lr;
+        k |= ((pos >> hi) & ((1 << lr) - 1)) << lo;
+        lo += lr;
+    }
+    return k;
+}
+template <int LOGLEN> __device__ __forceinline__ int digit_pos_ct(int k) {
+    int pos = 0, hi = LOGLEN, lo = 0;
+#pragma unroll
+    for (int i = 0; i < CtPlan<LOGLEN>::nst; ++i) {
+        const int lr = CtPlan<LOGLEN>::logr(i);
+        hi -= lr;
+        pos |= ((k >> lo) & ((1 << lr) - 1)) << hi;
+        lo += lr;
+    }
+    return pos;
+}
+
 struct RowLayoutCt {  // contiguous transform, one pad element per 16
     int row_stride;
     __device__ __forceinline__ int operator()(int b, int i) const { return b * row_stride + i + (i >> 4); }
@@ -50,14 +75,25 @@ __device__ __forceinline__ void stage_ct(float2* s, const Layout lay, const floa
         float2 x[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) x[q] = s[lay(b, base + (q << LOGSUB))];
+        // twiddles W_Lcur^(u p), p = 1..R-1.  Loading all of them costs R-1 LSU slots per
+        // butterfly (the kernels were MIO-throttled); instead p = 1,2,3 and 4,8,12 come from the
+        // table and the rest is one complex product each (<= 1.5e-7 relative error).
+        float2 wv[R];
+        if (LOGSUB > 0) {
+            const int ub = u << TWSHIFT;
+#pragma unroll
+            for (int p = 1; p < R; ++p) if (p < 4 || (p & 3) == 0) wv[p] = __ldg(tw + ub * p);
+#pragma unroll
+            for (int p = 5; p < R; ++p) if ((p & 3) != 0) wv[p] = cmul(wv[p & ~3], wv[p & 3]);
+        }
         if (DIR < 0 && LOGSUB > 0) {
 #pragma unroll
-            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], cconj(__ldg(tw + ((u * q) << TWSHIFT))));
+            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], cconj(wv[q]));
         }
         dft<R, DIR>(x);
         if (DIR > 0 && LOGSUB > 0) {
 #pragma unroll
-            for (int p = 1; p < R; ++p) x[p] = cmul(x[p], __ldg(tw + ((u * p) << TWSHIFT)));
+            for (int p = 1; p < R; ++p) x[p] = cmul(x[p], wv[p]);
         }
 #pragma unroll
         for (int p = 0; p < R; ++p) s[lay(b, base + (p << LOGSUB))] = x[p];
@@ -84,7 +120,7 @@ __device__ __forceinline__ void fft_inv_ct(float2* s, const Layout lay, const fl
 // ---------------------------------------------------------------- columns, forward --
 template <int LOGA, int LOGB, int LOGC, bool PADDED>
 __global__ void __launch_bounds__(kFastThreads, 3) k_fft_cols_ct(FftParams p) {
-    extern __shared__ float2 sm[];
+    extern __shared__ __align__(16) float2 sm[];
     constexpr int A = 1 << LOGA, C = 1 << LOGC;
     const int tid = threadIdx.x;
     const int j2_0 = blockIdx.x << LOGC;
@@ -103,18 +139,18 @@ __global__ void __launch_bounds__(kFastThreads, 3) k_fft_cols_ct(FftParams p) {
             v.z = 2 * j + 2 < p.n_valid ? __ldg(p.x + 2 * j + 2) : 0.f;
             v.w = 0.f;
         }
-        sm[lay(c2, j1)] = make_float2(v.x, v.y);
-        sm[lay(c2 + 1, j1)] = make_float2(v.z, v.w);
+        *reinterpret_cast<float4*>(&sm[lay(c2, j1)]) = v;  // (c2, c2+1) are adjacent and 16-byte aligned in this layout
     }
     __syncthreads();
     fft_fwd_ct<LOGA, 0, true, LOGC>(sm, lay, p.twA, tid);
 #pragma unroll 4
     for (int e = tid; e < A * HALF; e += kFastThreads) {
         const int row = e / HALF, c2 = (e - row * HALF) * 2;
-        const int k1 = __ldg(p.revA + row);
+        const int k1 = digit_rev_ct<LOGA>(row);
         const int j2 = j2_0 + c2;
-        const float2 a = cmul(sm[lay(c2, row)], twiddle_n(p, 2 * (int64_t)j2 * k1));          // W_M^(j2 k1) = W_N^(2 j2 k1)
-        const float2 b = cmul(sm[lay(c2 + 1, row)], twiddle_n(p, 2 * (int64_t)(j2 + 1) * k1));
+        const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, row)]);
+        const float2 a = cmul(make_float2(sv.x, sv.y), twiddle_n(p, 2 * (int64_t)j2 * k1));          // W_M^(j2 k1) = W_N^(2 j2 k1)
+        const float2 b = cmul(make_float2(sv.z, sv.w), twiddle_n(p, 2 * (int64_t)(j2 + 1) * k1));
         reinterpret_cast<float4*>(p.T)[(((int64_t)row << LOGB) + j2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
     }
 }
@@ -136,7 +172,7 @@ __device__ __forceinline__ void mid_pair(const FftParams& p, float2& zk_io, floa
 template <int LOGA, int LOGB, int LOGNB>
 __device__ __forceinline__ void mid_body(const FftParams& p, float2* sm, int k1a, int k1b, int tid) {
     constexpr int A = 1 << LOGA, B = 1 << LOGB, NR = 1 << LOGNB;
-    const int rowa = __ldg(p.posA + k1a), rowb = __ldg(p.posA + k1b);
+    const int rowa = digit_pos_ct<LOGA>(k1a), rowb = digit_pos_ct<LOGA>(k1b);
     const RowLayoutCt lay{B + (B >> 4) + 1};
     for (int e = tid; e < NR * (B / 2); e += kFastThreads) {
         const int r = e >> (LOGB - 1), i2 = (e & (B / 2 - 1)) * 2;
@@ -149,20 +185,20 @@ __device__ __forceinline__ void mid_body(const FftParams& p, float2* sm, int k1a
     const float sc = 0.5f * p.inv_scale;
     if (NR == 2) {
         for (int pos = tid; pos < B; pos += kFastThreads) {
-            const int k2 = __ldg(p.revB + pos);
-            const int pos2 = __ldg(p.posB + (B - 1 - k2));
+            const int k2 = digit_rev_ct<LOGB>(pos);
+            const int pos2 = digit_pos_ct<LOGB>(B - 1 - k2);
             mid_pair(p, sm[lay(0, pos)], sm[lay(1, pos2)], (int64_t)k1a + ((int64_t)k2 << LOGA), sc);
         }
     } else if (k1a == 0) {
         for (int k2 = tid; k2 <= B / 2; k2 += kFastThreads) {
-            const int pos = __ldg(p.posB + k2);
+            const int pos = digit_pos_ct<LOGB>(k2);
             if (k2 == 0) {
                 const float2 z = sm[lay(0, pos)];
                 const float P0 = (z.x + z.y) * (z.x + z.y), PM = (z.x - z.y) * (z.x - z.y);
                 sm[lay(0, pos)] = make_float2((P0 + PM) * sc, (P0 - PM) * sc);
                 continue;
             }
-            const int pos2 = __ldg(p.posB + (B - k2));
+            const int pos2 = digit_pos_ct<LOGB>(B - k2);
             float2 a = sm[lay(0, pos)], b = sm[lay(0, pos2)];
             mid_pair(p, a, b, (int64_t)k2 << LOGA, sc);
             sm[lay(0, pos)] = a;
@@ -170,7 +206,7 @@ __device__ __forceinline__ void mid_body(const FftParams& p, float2* sm, int k1a
         }
     } else {  // k1 = A/2: k2 <-> B-1-k2
         for (int k2 = tid; k2 < B / 2; k2 += kFastThreads) {
-            const int pos = __ldg(p.posB + k2), pos2 = __ldg(p.posB + (B - 1 - k2));
+            const int pos = digit_pos_ct<LOGB>(k2), pos2 = digit_pos_ct<LOGB>(B - 1 - k2);
             mid_pair(p, sm[lay(0, pos)], sm[lay(0, pos2)], (int64_t)k1a + ((int64_t)k2 << LOGA), sc);
         }
     }
@@ -191,7 +227,7 @@ __device__ __forceinline__ void mid_body(const FftParams& p, float2* sm, int k1a
 #endif
 template <int LOGA, int LOGB>
 __global__ void __launch_bounds__(kFastThreads, TSDR_FFT_MID_MINBLOCKS) k_fft_mid_ct(FftParams p) {
-    extern __shared__ float2 sm[];
+    extern __shared__ __align__(16) float2 sm[];
     constexpr int A = 1 << LOGA;
     const int k1a = blockIdx.x;
     const int k1b = (A - k1a) & (A - 1);
@@ -202,7 +238,7 @@ __global__ void __launch_bounds__(kFastThreads, TSDR_FFT_MID_MINBLOCKS) k_fft_mi
 // ---------------------------------------------------------------- columns, inverse --
 template <int LOGA, int LOGB, int LOGC>
 __global__ void __launch_bounds__(kFastThreads, 3) k_ifft_cols_ct(FftParams p) {
-    extern __shared__ float2 sm[];
+    extern __shared__ __align__(16) float2 sm[];
     constexpr int A = 1 << LOGA, C = 1 << LOGC, HALF = C / 2;
     const int tid = threadIdx.x;
     const int j2_0 = blockIdx.x << LOGC;
@@ -210,9 +246,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) k_ifft_cols_ct(FftParams p) {
 #pragma unroll 4
     for (int e = tid; e < A * HALF; e += kFastThreads) {
         const int row = e / HALF, c2 = (e - row * HALF) * 2;
-        const float4 v = reinterpret_cast<const float4*>(p.U)[(((int64_t)row << LOGB) + j2_0 + c2) >> 1];
-        sm[lay(c2, row)] = make_float2(v.x, v.y);
-        sm[lay(c2 + 1, row)] = make_float2(v.z, v.w);
+        *reinterpret_cast<float4*>(&sm[lay(c2, row)]) = reinterpret_cast<const float4*>(p.U)[(((int64_t)row << LOGB) + j2_0 + c2) >> 1];
     }
     __syncthreads();
     fft_inv_ct<LOGA, CtPlan<LOGA>::nst - 1, true, LOGC>(sm, lay, p.twA, tid);
@@ -223,8 +257,8 @@ __global__ void __launch_bounds__(kFastThreads, 3) k_ifft_cols_ct(FftParams p) {
         const int64_t j = ((int64_t)j1 << LOGB) + j2_0 + c2;
         const int64_t m0 = 2 * j;
         if (m0 > p.m_hi || m0 + 3 < p.m_lo) continue;
-        const float2 v0 = sm[lay(c2, j1)], v1 = sm[lay(c2 + 1, j1)];
-        float o[4] = {v0.x, v0.y, v1.x, v1.y};
+        const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, j1)]);
+        float o[4] = {sv.x, sv.y, sv.z, sv.w};
         if (!p.raw) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
