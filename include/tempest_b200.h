@@ -71,6 +71,16 @@ int tsdr_downgrade_f32(const float* img_colmajor, int y_t, int x_t, float* out_c
 /* naiveResampler(sigOut, sigId, upCoeff)         src/Resampler.jl:103-110 */
 int tsdr_naive_resampler_f32(float* out, const float* in, size_t n, int up);
 
+/* init_resampler(Float32, bufferSize, upCoeff) -> resampler!(out, in): FFT-domain integer upsampler
+ * (zero-stuff, FFT, * H, IFFT, 2*upCoeff*real).  src/Resampler.jl:26-62, filter from initLPF :83-99.
+ * The GPU FFT engine handles bufferSize*upCoeff = 2^k, 32 <= 2^k <= 2^24; other sizes return
+ * TSDR_ERR_UNSUPPORTED.  apply enforces the reference's size assertion (:47). */
+typedef struct tsdr_upsampler tsdr_upsampler;
+int tsdr_upsampler_create(size_t buffer_size, int up_coeff, tsdr_upsampler** out);
+int tsdr_upsampler_apply_f32(tsdr_upsampler* u, float* out, size_t n_out, const float* in, size_t n_in);
+int tsdr_upsampler_get_filter(tsdr_upsampler* u, double* H_interleaved /* bufferSize*upCoeff ComplexF64 */);
+int tsdr_upsampler_destroy(tsdr_upsampler* u);
+
 /* calculate_autocorrelation(x, Fs, minDelay, maxDelay, scale)
  * out receives indexMax-indexMin+1 values; *out_len is set to that count.
  * log_scale != 0 -> 10*log10(abs2(.)), else abs2(.).  src/Autocorrelations.jl:23-37 */

@@ -61,6 +61,10 @@ def _load():
         "orc_chain_buffer": (C.c_int, [_f32p, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_double, C.c_float,
                                        C.POINTER(_Sync), _f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
         "orc_num_threads": (C.c_int, []),
+        "orc_upsampler_create": (C.c_void_p, [C.c_size_t, C.c_int]),
+        "orc_upsampler_H": (None, [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")]),
+        "orc_upsampler_apply": (C.c_int, [C.c_void_p, _f32p, _f32p]),
+        "orc_upsampler_destroy": (None, [C.c_void_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -148,6 +152,25 @@ def naiveResampler(sig, up):  # src/Resampler.jl:103-110
     out = np.empty(sig.size * up, np.float32)
     lib.orc_naive_resampler(out, sig, sig.size, up)
     return out
+
+
+def init_resampler(bufferSize, upCoeff):  # src/Resampler.jl:26-62 (T = Float32) -> resampler(out, in)
+    h = lib.orc_upsampler_create(bufferSize, upCoeff)
+    if not h:
+        raise ValueError("bad upsampler size")
+    N = bufferSize * upCoeff
+
+    def resampler(out, sig):
+        sig = np.ascontiguousarray(sig, np.float32)
+        assert sig.size == bufferSize, "Size of input should match size used during init"   # :47
+        assert out.size == N and out.dtype == np.float32
+        if lib.orc_upsampler_apply(h, out, sig):
+            raise MemoryError
+    Hbuf = np.empty(2 * N, np.float64)
+    lib.orc_upsampler_H(h, Hbuf)
+    resampler.H = Hbuf.view(np.complex128)
+    resampler._handle = h
+    return resampler
 
 
 def fft(x, inverse=False):

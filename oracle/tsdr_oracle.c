@@ -189,6 +189,71 @@ void orc_naive_resampler(float* out, const float* in, size_t n, int up) { /* Res
         for (int k = 0; k < up; ++k) out[i * (size_t)up + k] = in[i];
 }
 
+/* init_resampler / resampler! (src/Resampler.jl:26-62) and initLPF (:83-99), T = Float32.
+ * H is built exactly as the reference does: brick-wall magnitude, linear phase ROUNDED to
+ * integers (round.(complex), :91), single-precision ifft, Blackman window (Float64), double-
+ * precision fft, (-1)^k.  resampler!: zero-stuff, Float32 FFT, ComplexF32*ComplexF64 product
+ * rounded to ComplexF32, scaled Float32 inverse FFT, out = 2*up*real(.). */
+struct orc_upsampler {
+    size_t n_in, N;
+    int up;
+    double* H;      /* N complex128, interleaved */
+};
+
+orc_upsampler* orc_upsampler_create(size_t buffer_size, int up) {
+    const size_t N = buffer_size * (size_t)up;
+    if (N < 2 || up < 1) return NULL;
+    orc_upsampler* u = (orc_upsampler*)calloc(1, sizeof(orc_upsampler));
+    u->n_in = buffer_size; u->N = N; u->up = up;
+    u->H = (double*)calloc(2 * N, sizeof(double));
+    orc_cf* Hs = (orc_cf*)calloc(N, sizeof(orc_cf));
+    orc_cf* hs = (orc_cf*)calloc(N, sizeof(orc_cf));
+    orc_cd* hd = (orc_cd*)calloc(N, sizeof(orc_cd));
+    const int64_t bound = orc_round_even((double)N / (double)up / 2.0);          /* :86 */
+    const double gd = -((double)N - 1.0) / 2.0;                                  /* :90 */
+    for (size_t k = 0; k < N; ++k) {
+        if ((int64_t)k < bound) {
+            const double puls = (double)((2.0L * 3.14159265358979323846264338327950288L * (long double)k) / (long double)N); /* :89 */
+            const double th = gd * puls;
+            Hs[k].re = (float)nearbyint(cos(th));                                /* round.(H .* exp.(im*gd*puls)) :91 */
+            Hs[k].im = (float)nearbyint(sin(th));
+        }
+    }
+    orcf_c2c(Hs, hs, N, 1);                                                      /* ifft(H) in ComplexF32 :95 */
+    for (size_t k = 0; k < N; ++k) {                                             /* .* blackman(N) (DSP.jl) */
+        const double x = (N > 1) ? (double)k / (double)(N - 1) - 0.5 : 0.0;
+        const double w = 0.42 + 0.5 * cos(2.0 * 3.14159265358979323846 * x) + 0.08 * cos(4.0 * 3.14159265358979323846 * x);
+        hd[k].re = (double)hs[k].re * w; hd[k].im = (double)hs[k].im * w;
+    }
+    orcd_c2c(hd, (orc_cd*)u->H, N, 0);                                           /* fft(h) in ComplexF64 :97 */
+    for (size_t k = 1; k < N; k += 2) { u->H[2 * k] = -u->H[2 * k]; u->H[2 * k + 1] = -u->H[2 * k + 1]; } /* .* (-1)^k */
+    free(Hs); free(hs); free(hd);
+    return u;
+}
+
+void orc_upsampler_H(const orc_upsampler* u, double* H_interleaved) { memcpy(H_interleaved, u->H, 2 * u->N * sizeof(double)); }
+
+int orc_upsampler_apply(orc_upsampler* u, float* out, const float* in) {        /* resampler! :42-60 */
+    const size_t N = u->N;
+    orc_cf* c = (orc_cf*)calloc(N, sizeof(orc_cf));
+    orc_cf* f = (orc_cf*)calloc(N, sizeof(orc_cf));
+    if (!c || !f) { free(c); free(f); return -1; }
+    for (size_t i = 0; i < u->n_in; ++i) c[i * (size_t)u->up].re = in[i];        /* containerFFT[1:up:end] .= in :48 */
+    orcf_c2c(c, f, N, 0);                                                        /* :49 */
+    for (size_t k = 0; k < N; ++k) {                                             /* inFFT[n] * H[n] :51-53 */
+        const double a = f[k].re, b = f[k].im, cc = u->H[2 * k], d = u->H[2 * k + 1];
+        f[k].re = (float)(a * cc - b * d);
+        f[k].im = (float)(a * d + b * cc);
+    }
+    orcf_c2c(f, c, N, 1);                                                        /* :55 */
+    const float g = (float)(2 * u->up);
+    for (size_t k = 0; k < N; ++k) out[k] = g * c[k].re;                         /* :57-59 */
+    free(c); free(f);
+    return 0;
+}
+
+void orc_upsampler_destroy(orc_upsampler* u) { if (!u) return; free(u->H); free(u); }
+
 /* ------------------------------------------------------------------------ */
 /* Autocorrelations.jl                                                       */
 /* ------------------------------------------------------------------------ */

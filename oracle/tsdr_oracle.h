@@ -43,7 +43,7 @@ void orc_naive_resampler(float* out, const float* in, size_t n, int up);        
 /* integer upsampler (init_resampler / resampler!), src/Resampler.jl:26-99 */
 typedef struct orc_upsampler orc_upsampler;
 orc_upsampler* orc_upsampler_create(size_t buffer_size, int up);
-void orc_upsampler_H(const orc_upsampler* u, float* H_interleaved); /* copy of H (complex64) */
+void orc_upsampler_H(const orc_upsampler* u, double* H_interleaved); /* copy of H (ComplexF64) */
 int orc_upsampler_apply(orc_upsampler* u, float* out, const float* in);
 void orc_upsampler_destroy(orc_upsampler* u);
 

@@ -31,6 +31,10 @@ SIGNATURES = {
     "tsdr_sig_to_image_f32": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_int, _vp]),
     "tsdr_downgrade_f32": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "tsdr_naive_resampler_f32": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int]),
+    "tsdr_upsampler_create": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(_vp)]),
+    "tsdr_upsampler_apply_f32": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t]),
+    "tsdr_upsampler_get_filter": (C.c_int, [_vp, _vp]),
+    "tsdr_upsampler_destroy": (C.c_int, [_vp]),
     "tsdr_autocorr_f32": (C.c_int, [_vp, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_int, _vp,
                                     C.POINTER(C.c_size_t)]),
     "tsdr_autocorr_out_len": (C.c_int, [C.c_size_t, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_size_t)]),

@@ -16,7 +16,7 @@ from .video_configurations import (VideoMode, allVideoConfigurations, find_close
                                    find_configuration, get_refresh_rates, dict2video)
 
 __all__ = [
-    "amDemod", "invert_amDemod", "fmDemod", "abs2", "sig_to_image", "downgradeImage", "naiveResampler",
+    "amDemod", "invert_amDemod", "fmDemod", "abs2", "sig_to_image", "downgradeImage", "naiveResampler", "init_resampler",
     "calculate_autocorrelation", "zoom_autocorr", "findmax", "SyncXY", "vsync", "fullScale",
     "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
     "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
@@ -93,6 +93,42 @@ def naiveResampler(sigOut, sigId, upCoeff):
         raise IndexError("BoundsError: sigOut shorter than upCoeff*length(sigId)")
     check(_lib.load().tsdr_naive_resampler_f32(_ptr(sigOut), _ptr(s), s.size, int(upCoeff)))
     return None
+
+
+def init_resampler(T, bufferSize, upCoeff=None):
+    """init_resampler(T, bufferSize, upCoeff) or init_resampler(x, upCoeff) -> resampler_(out, in)
+    -- src/Resampler.jl:26-68.  Only T = Float32 exists on the GPU; the closure enforces the
+    reference's type / size assertions (:44, :47)."""
+    if upCoeff is None:  # init_resampler(x::Vector{T}, upCoeff)  (:65-68)
+        x, upCoeff = T, bufferSize
+        T, bufferSize = np.asarray(x).dtype.type, len(x)
+    if np.dtype(T) != np.float32:
+        raise TypeError("libtempest_b200 implements init_resampler for Float32 only (got %s)" % np.dtype(T))
+    h = C.c_void_p()
+    check(_lib.load().tsdr_upsampler_create(int(bufferSize), int(upCoeff), C.byref(h)))
+    N = int(bufferSize) * int(upCoeff)
+
+    class _Closure:
+        def __init__(self):
+            self._h = h
+            Hb = np.empty(2 * N, np.float64)
+            check(_lib.load().tsdr_upsampler_get_filter(h, _ptr(Hb)))
+            self.H = Hb.view(np.complex128)
+
+        def __call__(self, out, sig):
+            if not isinstance(out, np.ndarray) or out.dtype != np.float32 or np.asarray(sig).dtype != np.float32:
+                raise AssertionError("Type of input should match type used during init (Float32)")   # :44
+            s = np.ascontiguousarray(sig)
+            if s.size != bufferSize:
+                raise AssertionError("Size of input %d should match size used during init %d" % (s.size, bufferSize))  # :47
+            check(_lib.load().tsdr_upsampler_apply_f32(self._h, _ptr(out), out.size, _ptr(s), s.size))
+
+        def __del__(self):
+            if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "load", None):
+                _lib.load().tsdr_upsampler_destroy(self._h)
+                self._h = None
+
+    return _Closure()
 
 
 def _round(x):  # Base.round, ties to even

@@ -183,6 +183,13 @@ struct FftParams {
     int64_t m_lo, m_hi;    // 0-based lag range to write
     int log_scale;
     int raw;               // write r (not r^2 / dB): used by the fold path
+    // mode 1: FFT-domain integer upsampler (init_resampler / resampler!, src/Resampler.jl:26-62):
+    // complex transform of the zero-stuffed real input, spectrum * H, inverse, gain * real part
+    int mode;
+    int up;                // zero-stuffing factor
+    int64_t n_in;          // input samples (M = n_in * up)
+    const double2* Hd;     // [M] filter in ComplexF64, natural frequency order
+    float gain;            // 2 * upCoeff
 };
 
 __device__ __forceinline__ float2 twiddle_n(const FftParams& p, int64_t t) {  // W_N^t, 0 <= t < N
@@ -207,7 +214,11 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_cols(FftParams p) {
         const int j1 = e / p.C, col = e - j1 * p.C;
         const int64_t j = (int64_t)j1 * p.B + j2_0 + col;
         float2 v;
-        if (2 * j + 1 < p.n_valid) v = __ldg(reinterpret_cast<const float2*>(p.x) + j);
+        if (p.mode == 1) {  // containerFFT[1:upCoeff:end] .= in   (Resampler.jl:48)
+            const int64_t q = j / p.up;
+            v.x = (q * p.up == j && q < p.n_in) ? __ldg(p.x + q) : 0.f;
+            v.y = 0.f;
+        } else if (2 * j + 1 < p.n_valid) v = __ldg(reinterpret_cast<const float2*>(p.x) + j);
         else { v.x = (2 * j < p.n_valid) ? __ldg(p.x + 2 * j) : 0.f; v.y = 0.f; }
         sm[lay(col, j1)] = v;
     }
@@ -244,7 +255,18 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_mid(FftParams p) {
 
     // real-input unpack, |X|^2, Hermitian repack (pairs k <-> M-k), scaled by 1/M
     const float sc = 0.5f * p.inv_scale;
-    if (!self) {
+    if (p.mode == 1) {
+        // inFFT[n] = inFFT[n] * H[n]: ComplexF32 * ComplexF64 in Float64, rounded to ComplexF32 (Resampler.jl:51-53);
+        // the 1/M of the scaled inverse plan is applied here
+        for (int e = tid; e < nrows * p.B; e += kFftThreads) {
+            const int r = e / p.B, pos = e - r * p.B;
+            const int64_t k = (int64_t)(r == 0 ? k1a : k1b) + (int64_t)p.A * __ldg(p.revB + pos);
+            const double2 h = __ldg(p.Hd + k);
+            const float2 z = sm[lay(r, pos)];
+            const double a = (double)z.x, b = (double)z.y;
+            sm[lay(r, pos)] = make_float2((float)(a * h.x - b * h.y) * p.inv_scale, (float)(a * h.y + b * h.x) * p.inv_scale);
+        }
+    } else if (!self) {
         for (int pos = tid; pos < p.B; pos += kFftThreads) {
             const int k2 = __ldg(p.revB + pos);
             const int pos2 = __ldg(p.posB + (p.B - 1 - k2));
@@ -329,6 +351,7 @@ __global__ void __launch_bounds__(kFftThreads) k_ifft_cols(FftParams p) {
     for (int e = tid; e < total; e += kFftThreads) {
         const int j1 = e / p.C, col = e - j1 * p.C;
         const int64_t j = (int64_t)j1 * p.B + j2_0 + col;
+        if (p.mode == 1) { p.out[j] = p.gain * sm[lay(col, j1)].x; continue; }  // out[n] = 2*upCoeff*real(outFFT[n])  (Resampler.jl:57-59)
         const int64_t m0 = 2 * j;
         if (m0 > p.m_hi || m0 + 1 < p.m_lo) continue;
         const float2 v = sm[lay(col, j1)];
@@ -541,6 +564,129 @@ int tsdr_autocorr_plan_exec(tsdr_autocorr_plan* p, const float* x_dev, size_t in
 int tsdr_autocorr_plan_launch_count(tsdr_autocorr_plan* p, uint64_t* count) {
     TSDR_REQUIRE(p && count, "NULL argument");
     *count = p->launches;
+    return TSDR_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ upsampler (R3) --
+namespace tsdr {
+// host-side radix-2 FFT in double (power-of-two lengths), used once at init to build H
+static void host_fft(std::vector<double>& re, std::vector<double>& im, bool inverse) {
+    const size_t n = re.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+    const double PI = 3.14159265358979323846264338327950288;
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const double ang = (inverse ? 2.0 : -2.0) * PI / (double)len;
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const double wr = cos(ang * (double)k), wi = sin(ang * (double)k);
+                const size_t a = i + k, b = i + k + len / 2;
+                const double tr = re[b] * wr - im[b] * wi, ti = re[b] * wi + im[b] * wr;
+                re[b] = re[a] - tr; im[b] = im[a] - ti;
+                re[a] += tr; im[a] += ti;
+            }
+    }
+    if (inverse) for (size_t i = 0; i < n; ++i) { re[i] /= (double)n; im[i] /= (double)n; }
+}
+}  // namespace tsdr
+
+struct tsdr_upsampler {
+    tsdr_autocorr_plan* plan;  // complex M-point engine (M = buffer_size * up)
+    size_t n_in, M;
+    int up;
+    double2* d_H;
+    float* d_in; float* d_out;
+    std::vector<double>* H;    // host copy, interleaved
+};
+
+extern "C" {
+
+int tsdr_upsampler_destroy(tsdr_upsampler* u) {
+    if (!u) return TSDR_OK;
+    if (u->plan) { cudaSetDevice(u->plan->device); cudaStreamSynchronize(u->plan->stream); }
+    cudaFree(u->d_H); cudaFree(u->d_in); cudaFree(u->d_out);
+    tsdr_autocorr_plan_destroy(u->plan);
+    delete u->H;
+    delete u;
+    return TSDR_OK;
+}
+
+int tsdr_upsampler_create(size_t buffer_size, int up_coeff, tsdr_upsampler** out) {
+    TSDR_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    TSDR_REQUIRE(buffer_size >= 1 && up_coeff >= 1, "bufferSize and upCoeff must be positive");
+    const size_t M = buffer_size * (size_t)up_coeff;
+    if (!is_pow2(M) || M < 32 || M > ((size_t)1 << 24)) {
+        set_error("init_resampler: bufferSize*upCoeff = %zu is not a power of two in [32, 2^24]; the GPU FFT engine "
+                  "only handles those lengths", M);
+        return TSDR_ERR_UNSUPPORTED;
+    }
+    int rc = ensure_device(); if (rc) return rc;
+    tsdr_upsampler* u = new (std::nothrow) tsdr_upsampler();
+    if (!u) return TSDR_ERR_NOMEM;
+    memset(u, 0, sizeof(*u));
+    u->n_in = buffer_size; u->M = M; u->up = up_coeff;
+    if ((rc = tsdr_autocorr_plan_create(&u->plan, current_device(), 2 * M, nullptr))) { tsdr_upsampler_destroy(u); return rc; }
+    // initLPF (src/Resampler.jl:83-99): brick-wall magnitude, linear phase rounded to integers,
+    // ifft, Blackman window, fft, (-1)^k.  (The reference's ifft runs in Float32; here it is
+    // evaluated in double and rounded to Float32, a <= 1e-7 relative difference in h.)
+    std::vector<double> re(M, 0.0), im(M, 0.0);
+    const int64_t bound = round_even((double)M / (double)up_coeff / 2.0);
+    const double gd = -((double)M - 1.0) / 2.0;
+    for (size_t k = 0; k < M && (int64_t)k < bound; ++k) {
+        const double puls = (double)((2.0L * 3.14159265358979323846264338327950288L * (long double)k) / (long double)M);
+        const double th = gd * puls;
+        re[k] = nearbyint(cos(th)); im[k] = nearbyint(sin(th));
+    }
+    host_fft(re, im, true);
+    for (size_t k = 0; k < M; ++k) {
+        const double x = (double)k / (double)(M - 1) - 0.5;
+        const double w = 0.42 + 0.5 * cos(2.0 * 3.14159265358979323846 * x) + 0.08 * cos(4.0 * 3.14159265358979323846 * x);
+        re[k] = (double)(float)re[k] * w; im[k] = (double)(float)im[k] * w;
+    }
+    host_fft(re, im, false);
+    u->H = new std::vector<double>(2 * M);
+    for (size_t k = 0; k < M; ++k) { const double sg = (k & 1) ? -1.0 : 1.0; (*u->H)[2 * k] = sg * re[k]; (*u->H)[2 * k + 1] = sg * im[k]; }
+    cudaError_t e = cudaMalloc(&u->d_H, M * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&u->d_in, (buffer_size + 4) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&u->d_out, M * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(u->d_H, u->H->data(), M * sizeof(double2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { tsdr_upsampler_destroy(u); return cuda_fail(e, "tsdr_upsampler_create", __FILE__, __LINE__); }
+    *out = u;
+    return TSDR_OK;
+}
+
+int tsdr_upsampler_get_filter(tsdr_upsampler* u, double* H_interleaved) {
+    TSDR_REQUIRE(u && H_interleaved, "NULL argument");
+    memcpy(H_interleaved, u->H->data(), 2 * u->M * sizeof(double));
+    return TSDR_OK;
+}
+
+int tsdr_upsampler_apply_f32(tsdr_upsampler* u, float* out, size_t n_out, const float* in, size_t n_in) {
+    TSDR_REQUIRE(u && out && in, "NULL argument");
+    // the reference's @assert (src/Resampler.jl:47): input length must match the init size
+    TSDR_REQUIRE(n_in == u->n_in, "Size of input %zu should match size used during init %zu", n_in, u->n_in);
+    TSDR_REQUIRE(n_out >= u->M, "output holds %zu samples, need bufferSize*upCoeff = %zu", n_out, u->M);
+    tsdr_autocorr_plan* p = u->plan;
+    TSDR_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    TSDR_CUDA(cudaMemcpyAsync(u->d_in, in, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
+    FftParams fp = p->fp;
+    fp.mode = 1; fp.x = u->d_in; fp.n_in = (int64_t)u->n_in; fp.up = u->up; fp.Hd = u->d_H;
+    fp.gain = (float)(2 * u->up); fp.out = u->d_out; fp.n_valid = 0;
+    k_fft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
+    k_fft_mid<<<fp.A / 2 + 1, kFftThreads, p->smem_mid, st>>>(fp);
+    k_ifft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
+    p->launches += 3;
+    TSDR_CUDA(cudaGetLastError());
+    TSDR_CUDA(cudaMemcpyAsync(out, u->d_out, u->M * sizeof(float), cudaMemcpyDeviceToHost, st));
+    TSDR_CUDA(cudaStreamSynchronize(st));
     return TSDR_OK;
 }
 

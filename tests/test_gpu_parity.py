@@ -77,6 +77,25 @@ def test_naiveResampler():
     assert np.array_equal(out, orc.naiveResampler(s, 3))
 
 
+@pytest.mark.parametrize("n,up", [(256, 4), (1024, 8), (4096, 2), (16, 2)])
+def test_init_resampler_matches_oracle(n, up):
+    t = np.arange(n) / n
+    x = (np.sin(2 * np.pi * 5 * t) + 0.5 * np.cos(2 * np.pi * 11 * t) + 0.1 * np.random.default_rng(n).normal(size=n)).astype(np.float32)
+    ref_fn = orc.init_resampler(n, up)
+    got_fn = tsdr.init_resampler(np.float32, n, up)
+    np.testing.assert_allclose(got_fn.H, ref_fn.H, rtol=0, atol=2e-6)   # H: Float32 ifft in the reference vs double here
+    ref = np.zeros(n * up, np.float32)
+    got = np.zeros(n * up, np.float32)
+    ref_fn(ref, x)
+    got_fn(got, x)
+    # stated tolerance: Float32 FFT round-off, 1e-5 of the signal's peak
+    assert np.max(np.abs(got - ref)) <= 1e-5 * np.max(np.abs(ref))
+    with pytest.raises(AssertionError):
+        got_fn(got, x[:-1])                      # size assertion of the reference (Resampler.jl:47)
+    with pytest.raises(tsdr.TempestError):
+        tsdr.init_resampler(np.float32, 100, 3)  # 300 is not a power of two: unsupported on the GPU engine
+
+
 def test_fullScale_findmax():
     m = np.random.default_rng(3).normal(size=(600, 800)).astype(np.float32)
     assert np.array_equal(tsdr.fullScale(m), orc.fullScale(m))
