@@ -286,14 +286,15 @@ class Chain:
         z, n = _iq(iq)
         nf = C.c_int(0)
         check(_lib.load().tsdr_chain_push_host(self._h, _ptr(z), n, C.byref(nf)))
-        self._keep = z  # the copy is asynchronous: keep the buffer alive until the next sync
+        # the H2D copy is asynchronous and double buffered: keep the last two host buffers alive
+        self._keep = [z] + list(getattr(self, "_keep", []))[:1]
         return nf.value
 
     def prime(self, iq):
         """advance only the SyncXY state with these frames (halo frame of a sharded integration)"""
         z, n = _iq(iq)
         check(_lib.load().tsdr_chain_prime_host(self._h, _ptr(z), n))
-        self._keep = z
+        self._keep = [z] + list(getattr(self, "_keep", []))[:1]
 
     def push_host_ptr(self, ptr, n):
         nf = C.c_int(0)

@@ -415,6 +415,13 @@ __global__ void __launch_bounds__(256) k_selftest_hypot(unsigned long long n, un
         const float f = dev_hypotf(x, y), g = dev_hypotf_ieee(x, y);
         const bool same = (__float_as_uint(f) == __float_as_uint(g)) || (f != f && g != g);
         local += same ? 0 : 1;
+        // packed two-sample version: (x, y) paired with (y, x*0.75) so both lanes carry fresh data
+        const float x2 = y, y2 = __fmul_rn(x, 0.75f);
+        const float2 pr = dev_hypot_pair(make_float4(x, y, x2, y2));
+        const float g2 = dev_hypotf_ieee(x2, y2);
+        const bool same2 = ((__float_as_uint(pr.x) == __float_as_uint(g)) || (pr.x != pr.x && g != g)) &&
+                           ((__float_as_uint(pr.y) == __float_as_uint(g2)) || (pr.y != pr.y && g2 != g2));
+        local += same2 ? 0 : 1;
     }
     if (local) atomicAdd(bad, local);
 }
@@ -565,6 +572,9 @@ struct tsdr_chain {
     bool own_stream;
     cudaStream_t aux;      // high-priority stream: projections, sync search, accumulate of the previous buffer
     cudaEvent_t ev_render[2], ev_free[2], ev_join;
+    cudaStream_t copy;     // H2D copies of tsdr_chain_push_host, overlapped with the previous buffer's kernels
+    cudaEvent_t ev_copied[2], ev_staging_free[2];
+    int stage_parity;
     int parity;            // which of the two frame buffers the next push renders into
     bool aux_busy;         // work queued on aux since the last join
     double Fs, fv;
@@ -579,7 +589,7 @@ struct tsdr_chain {
     SyncParams sp;
     size_t smem_bytes;
     // device memory
-    float* d_iq;        // staging for push_host (max_samples + pad)
+    float* d_iq2[2];    // two staging buffers for push_host (max_samples + pad each)
     float* d_frames2[2]; // 2 x [max_frames][600][800]: render of buffer b+1 overlaps the sync/accumulate of buffer b
     float* d_published; // optional
     float* d_acc;       // imageOut, scan order
@@ -826,7 +836,13 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_iq, (max_samples + 2) * 8);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_staging_free[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_iq2[i], (max_samples + 2) * 8);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_iq2[i], 0, (max_samples + 2) * 8, c->stream);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&c->d_acc, (size_t)kRenderN * 4);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tmp, (size_t)kRenderN * 4);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_fy, kRenderH * sizeof(int));
@@ -836,7 +852,6 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
     if (e == cudaSuccess) e = cudaMalloc(&c->d_win_len, kRenderH * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_dx, kRenderW * sizeof(double));
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_acc, 0, (size_t)kRenderN * 4, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_iq, 0, (max_samples + 2) * 8, c->stream);
     if (e != cudaSuccess) rc = cuda_fail(e, "tsdr_chain_create", __FILE__, __LINE__);
     if (rc == TSDR_OK) rc = chain_setup(c, Fs, x_t, y_t, fv);
     if (rc != TSDR_OK) { tsdr_chain_destroy(c); return rc; }
@@ -870,14 +885,36 @@ int tsdr_chain_reset(tsdr_chain* c) {
     return TSDR_OK;
 }
 
+namespace tsdr {
+// H2D copy of a host buffer into the next staging buffer on the copy stream; the primary
+// stream only waits for THIS copy, so it overlaps the kernels of the previous buffer.
+static int chain_stage(tsdr_chain* c, const float* iq_host, size_t n, float** staged) {
+    const int sp = c->stage_parity;
+    c->stage_parity ^= 1;
+    // only the samples of complete frames are used (GUI.jl:137,165-166)
+    const size_t used = (n / (size_t)c->S) * (size_t)c->S;
+    if (used) {
+        TSDR_CUDA(cudaStreamWaitEvent(c->copy, c->ev_staging_free[sp], 0));  // render of the push before last has read it
+        TSDR_CUDA(cudaMemcpyAsync(c->d_iq2[sp], iq_host, used * 8, cudaMemcpyHostToDevice, c->copy));
+        TSDR_CUDA(cudaEventRecord(c->ev_copied[sp], c->copy));
+        TSDR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[sp], 0));
+    }
+    *staged = c->d_iq2[sp];
+    return TSDR_OK;
+}
+}  // namespace tsdr
+
 int tsdr_chain_push_host(tsdr_chain* c, const float* iq_host, size_t n, int* n_frames) {
     TSDR_REQUIRE(c && (iq_host || n == 0), "NULL argument");
     TSDR_REQUIRE(n <= c->max_samples, "buffer of %zu samples exceeds max_samples %zu", n, c->max_samples);
     TSDR_CUDA(cudaSetDevice(c->device));
-    // only the samples of complete frames are used (GUI.jl:137,165-166)
-    const size_t used = (n / (size_t)c->S) * (size_t)c->S;
-    if (used) TSDR_CUDA(cudaMemcpyAsync(c->d_iq, iq_host, used * 8, cudaMemcpyHostToDevice, c->stream));
-    return chain_run(c, c->d_iq, n, n_frames);
+    float* staged = nullptr;
+    int rc = chain_stage(c, iq_host, n, &staged);
+    if (rc) return rc;
+    const int sp = c->stage_parity ^ 1;
+    rc = chain_run(c, staged, n, n_frames);
+    if (rc == TSDR_OK && n / (size_t)c->S) TSDR_CUDA(cudaEventRecord(c->ev_staging_free[sp], c->stream));
+    return rc;
 }
 
 int tsdr_chain_prime_host(tsdr_chain* c, const float* iq_host, size_t n) {
@@ -885,9 +922,13 @@ int tsdr_chain_prime_host(tsdr_chain* c, const float* iq_host, size_t n) {
     TSDR_REQUIRE(n <= c->max_samples, "buffer of %zu samples exceeds max_samples %zu", n, c->max_samples);
     TSDR_REQUIRE(!(c->flags & TSDR_CHAIN_NO_ALIGN), "priming is meaningless without frame alignment");
     TSDR_CUDA(cudaSetDevice(c->device));
-    const size_t used = (n / (size_t)c->S) * (size_t)c->S;
-    if (used) TSDR_CUDA(cudaMemcpyAsync(c->d_iq, iq_host, used * 8, cudaMemcpyHostToDevice, c->stream));
-    return chain_run(c, c->d_iq, n, nullptr, true);
+    float* staged = nullptr;
+    int rc = chain_stage(c, iq_host, n, &staged);
+    if (rc) return rc;
+    const int sp = c->stage_parity ^ 1;
+    rc = chain_run(c, staged, n, nullptr, true);
+    if (rc == TSDR_OK && n / (size_t)c->S) TSDR_CUDA(cudaEventRecord(c->ev_staging_free[sp], c->stream));
+    return rc;
 }
 
 int tsdr_chain_push_device(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames) {
@@ -1035,7 +1076,14 @@ int tsdr_chain_destroy(tsdr_chain* c) {
     if (c->ev_pool) { for (cudaEvent_t ev : *c->ev_pool) cudaEventDestroy(ev); delete c->ev_pool; }
     if (c->ev_marks) { for (cudaEvent_t ev : *c->ev_marks) cudaEventDestroy(ev); delete c->ev_marks; }
     tsdr::chain_free_frames(c);
-    cudaFree(c->d_iq); cudaFree(c->d_acc); cudaFree(c->d_tmp);
+    if (c->copy) cudaStreamSynchronize(c->copy);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_iq2[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_staging_free[i]) cudaEventDestroy(c->ev_staging_free[i]);
+    }
+    if (c->copy) cudaStreamDestroy(c->copy);
+    cudaFree(c->d_acc); cudaFree(c->d_tmp);
     cudaFree(c->d_fy); cudaFree(c->d_dy); cudaFree(c->d_kd); cudaFree(c->d_dx); cudaFree(c->d_win_lo); cudaFree(c->d_win_len);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
