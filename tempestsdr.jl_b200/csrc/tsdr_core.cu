@@ -415,13 +415,6 @@ __global__ void __launch_bounds__(256) k_selftest_hypot(unsigned long long n, un
         const float f = dev_hypotf(x, y), g = dev_hypotf_ieee(x, y);
         const bool same = (__float_as_uint(f) == __float_as_uint(g)) || (f != f && g != g);
         local += same ? 0 : 1;
-        // packed two-sample version: (x, y) paired with (y, x*0.75) so both lanes carry fresh data
-        const float x2 = y, y2 = __fmul_rn(x, 0.75f);
-        const float2 pr = dev_hypot_pair(make_float4(x, y, x2, y2));
-        const float g2 = dev_hypotf_ieee(x2, y2);
-        const bool same2 = ((__float_as_uint(pr.x) == __float_as_uint(g)) || (pr.x != pr.x && g != g)) &&
-                           ((__float_as_uint(pr.y) == __float_as_uint(g2)) || (pr.y != pr.y && g2 != g2));
-        local += same2 ? 0 : 1;
     }
     if (local) atomicAdd(bad, local);
 }
