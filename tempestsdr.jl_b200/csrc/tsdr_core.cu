@@ -3,6 +3,7 @@
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false
 #include "tsdr_kernels.cuh"
 
+#include <algorithm>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -662,6 +663,17 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         win_lo[i] = (int)flo; win_len[i] = W;
         if (W > win) win = W;
     }
+    // G output rows per CTA: as many as keep the staged window under ~20 KB (small windows are
+    // dominated by per-CTA fixed cost); the window of a group is the union of its rows' windows
+    int G = 1;
+    for (int cand = 2; cand <= 8; cand *= 2) {
+        int wmax = 0;
+        for (int r0 = 0; r0 < kRenderH; r0 += cand) {
+            const int r1 = std::min(r0 + cand, kRenderH) - 1;
+            wmax = std::max(wmax, win_lo[r1] + win_len[r1] - win_lo[r0]);
+        }
+        if ((size_t)(wmax + 4) * sizeof(double) <= 20 * 1024) { G = cand; win = std::max(win, wmax); }
+    }
     const size_t smem = (size_t)(win + 4) * sizeof(double);
     if (smem > 200 * 1024) {
         set_error("frame window of %d samples does not fit shared memory (Fs/fv/y_t = %.1f samples per line)", win,
@@ -719,6 +731,7 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         if (!(raw(rp.safe_lo) >= 1.0) || !(raw(rp.safe_hi) < (double)S)) { rp.safe_lo = 1.0; rp.safe_hi = 0.0; }  // every CTA takes the exact path
     }
     rp.fx_first = fx[0]; rp.fx_last = fx[kRenderW - 1];
+    rp.rows_per_cta = G;
     rp.frames = nullptr;  // set per push
     TSDR_CUDA(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TSDR_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProjSmem));
@@ -769,7 +782,7 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     rp.iq = iq_dev; rp.n_ech = (int64_t)n; rp.frames = c->d_frames2[par];
     if (piped) TSDR_CUDA(cudaStreamWaitEvent(st, c->ev_free[par], 0));  // frames[par] released by the push before last
     mark(st);
-    dim3 grid(kRenderH, nb);
+    dim3 grid((kRenderH + rp.rows_per_cta - 1) / rp.rows_per_cta, nb);
     k_render<<<grid, kRenderThreads, c->smem_bytes, st>>>(rp);
     c->launches += 1;
     mark(st);
