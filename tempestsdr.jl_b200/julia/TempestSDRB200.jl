@@ -11,7 +11,7 @@
 # plain column-major Julia Arrays, ComplexF32 vectors are passed as they are (interleaved re, im).
 module TempestSDRB200
 
-export amDemod, invert_amDemod, sig_to_image, downgradeImage, naiveResampler,
+export amDemod, invert_amDemod, sig_to_image, downgradeImage, naiveResampler, init_resampler,
        calculate_autocorrelation, zoom_autocorr, SyncXY, vsync, Chain, push!, image, offsets
 
 const LIB = get(ENV, "TEMPEST_B200_LIB", joinpath(@__DIR__, "..", "libtempest_b200.so"))
@@ -71,6 +71,22 @@ function naiveResampler(sigOut::Vector{Float32}, sigId::Vector{Float32}, upCoeff
                                           pointer(sigOut), pointer(sigId), length(sigId), upCoeff))
     return nothing
 end
+
+# init_resampler(T, bufferSize, upCoeff) -> resampler!(out, in)                 src/Resampler.jl:26-62
+function init_resampler(T::Type, bufferSize::Int, upCoeff::Int)
+    T === Float32 || error("libtempest_b200 implements init_resampler for Float32 only")
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:tsdr_upsampler_create, LIB), Cint, (Csize_t, Cint, Ptr{Ptr{Cvoid}}), bufferSize, upCoeff, h))
+    handle = h[]
+    function resampler!(out::AbstractVector{T2}, in::AbstractVector{T2}) where T2
+        @assert T == T2 "Type of input ($T2) should match type used during init ($T)"
+        @assert length(in) == bufferSize "Size of input $(length(in)) should match size used during init $bufferSize"
+        GC.@preserve out in check(ccall((:tsdr_upsampler_apply_f32, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}, Csize_t),
+                                        handle, pointer(out), length(out), pointer(in), length(in)))
+    end
+    return resampler!
+end
+init_resampler(x::Vector{T}, upCoeff) where T = init_resampler(T, length(x), upCoeff)
 
 # ---- Autocorrelations.jl -------------------------------------------------------------------
 function calculate_autocorrelation(x::Vector{Float32}, Fs, minDelay, maxDelay, scale = :log)   # :23-37
@@ -173,7 +189,7 @@ set_alpha!(c::Chain, α) = check(ccall((:tsdr_chain_set_alpha, LIB), Cint, (Ptr{
 
 # Rebind the reference module's DSP functions to the GPU versions (same names, same signatures).
 function use!(ref::Module)
-    for f in (:amDemod, :invert_amDemod, :sig_to_image, :downgradeImage, :naiveResampler,
+    for f in (:amDemod, :invert_amDemod, :sig_to_image, :downgradeImage, :naiveResampler, :init_resampler,
               :calculate_autocorrelation, :zoom_autocorr, :vsync)
         Core.eval(ref, :($f(args...; kw...) = $(getfield(TempestSDRB200, f))(args...; kw...)))
     end
