@@ -18,6 +18,7 @@
 // N >= 2n and fold the linear lags: r_circ[k] = r_lin[k] + r_lin[n-k].
 #include "tsdr_internal.cuh"
 
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -381,6 +382,7 @@ __global__ void __launch_bounds__(256) k_fold_lags(const float* __restrict__ lin
 }  // namespace tsdr
 
 #include "tsdr_fft_fast.cuh"
+#include "tsdr_fft3.cuh"
 
 using namespace tsdr;
 
@@ -395,6 +397,8 @@ struct tsdr_autocorr_plan {
     size_t smem_cols, smem_mid;
     bool has_fast;
     FastKernels fast;
+    bool has_fft3;
+    Fft3Kernels f3;
     uint64_t launches;
     void* d_tables;  // one allocation for every table
     float2* d_T; float2* d_U;
@@ -514,6 +518,17 @@ int tsdr_autocorr_plan_create(tsdr_autocorr_plan** out, int device, size_t n, vo
         int loga = 0, logb = 0;
         while ((1 << loga) < A) ++loga;
         while ((1 << logb) < B) ++logb;
+        int logN = 0;
+        while (((size_t)1 << logN) < p->N) ++logN;
+        p->has_fft3 = find_fft3(logN, logb, &p->f3);
+        if (p->has_fft3 && e == cudaSuccess) {
+            e = cudaFuncSetAttribute(p->f3.p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p1);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p1_padded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p1);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p1);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p2);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p2);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p3);
+        }
         p->has_fast = find_fast(loga, logb, &p->fast);
         if (p->has_fast && e == cudaSuccess) {
             e = cudaFuncSetAttribute(p->fast.cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast.smem_cols);
@@ -540,7 +555,15 @@ int tsdr_autocorr_plan_exec(tsdr_autocorr_plan* p, const float* x_dev, size_t in
     if (p->fold) { fp.out = p->d_lin; fp.m_lo = 0; fp.m_hi = (int64_t)p->n; fp.raw = 1; }
     else { fp.out = out_dev; fp.m_lo = (int64_t)index_min - 1; fp.m_hi = (int64_t)index_max - 1; fp.raw = 0; }
     cudaStream_t st = p->stream;
-    if (p->has_fast && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) {
+    if (p->has_fft3 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 && !getenv("TSDR_FFT_TWO_LEVEL")) {
+        if (p->n == p->N) p->f3.p1<<<p->f3.grid_p1, kFastThreads, p->f3.smem_p1, st>>>(fp);
+        else p->f3.p1_padded<<<p->f3.grid_p1, kFastThreads, p->f3.smem_p1, st>>>(fp);
+        p->f3.p2<<<p->f3.grid_p2, kFastThreads, p->f3.smem_p2, st>>>(fp);
+        p->f3.p3<<<p->f3.grid_p3, kFastThreads, p->f3.smem_p3, st>>>(fp);
+        p->f3.p4<<<p->f3.grid_p2, kFastThreads, p->f3.smem_p2, st>>>(fp);
+        p->f3.p5<<<p->f3.grid_p1, kFastThreads, p->f3.smem_p1, st>>>(fp);
+        p->launches += 2;
+    } else if (p->has_fast && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) {
         const int grid_cols = fp.B >> p->fast.logc;
         if (p->n == p->N) p->fast.cols<<<grid_cols, kFastThreads, p->fast.smem_cols, st>>>(fp);
         else p->fast.cols_padded<<<grid_cols, kFastThreads, p->fast.smem_cols, st>>>(fp);

@@ -1,0 +1,278 @@
+// tsdr_fft3.cuh -- three-level autocorrelation FFT for the large sizes (included by tsdr_fft.cu
+// after tsdr_fft_fast.cuh).
+//
+// The two-level kernels read and write 32-byte pieces at 32 KB stride in their column passes
+// (1.2 TB/s effective).  Here the M = N/2 complex points are viewed as D[a][b][c]
+// (NA x NB x NC, c fastest) and every pass moves >= 128 contiguous bytes:
+//   P1  FFT over a for tiles of C1 consecutive (b,c)   * W_M^(ka r)       x  -> T   (natural ka)
+//   P2  FFT over b for tiles of C2 consecutive c       * W_M'^(kb c)      T in place (natural kb)
+//   P3  rows over c: FFT, real-input unpack, |X|^2, Hermitian repack, inverse FFT, * conj W_M'^(kb c)
+//   P4  inverse FFT over kb, * conj W_M^(ka r)                            T in place
+//   P5  inverse FFT over ka, epilogue 10 log10(r^2) over the requested lags          T -> out
+// Rows/columns are stored in NATURAL frequency order between passes (the digit reversal of the
+// in-place DIF/DIT butterflies stays inside shared memory), and P2..P4 work in place, so the
+// whole working set is one M-point buffer (64 MB at n = 2^24) that fits the 126 MB L2.
+//
+// Frequency index: k = ka + NA (kb + NB kc).  Mirror M-k used by the real-input unpack:
+//   ka > 0          : (NA-ka, NB-1-kb, NC-1-kc)   -> row rho = ka NB + kb  pairs with  NA NB + NB - 1 - rho
+//   ka = 0, kb > 0  : (0, NB-kb, NC-1-kc)
+//   ka = 0, kb = 0  : (0, 0, (NC-kc) mod NC)
+#pragma once
+
+namespace tsdr {
+
+template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB>
+struct Fft3 {
+    static constexpr int NA = 1 << LOGNA, NB = 1 << LOGNB, NC = 1 << LOGNC;
+    static constexpr int LOGNBC = LOGNB + LOGNC;
+    static constexpr int R = 1 << LOGR;
+    static constexpr int kRowStride = NC + (NC >> 4) + 1;
+    static constexpr size_t smem_p1 = (size_t)col_padded_ct<LOGC1>(NA << LOGC1) * sizeof(float2);
+    static constexpr size_t smem_p2 = (size_t)col_padded_ct<LOGC2>(NB << LOGC2) * sizeof(float2);
+    static constexpr size_t smem_p3 = (size_t)2 * R * kRowStride * sizeof(float2);
+    static constexpr int grid_p1 = (1 << LOGNBC) >> LOGC1;
+    static constexpr int grid_p2 = NA << (LOGNC - LOGC2);
+    static constexpr int n_regular = (NB / 2) * (NA - 1) / R;          // row pairs with ka > 0
+    static constexpr int n_special = (NB / 2 + 1 + R - 1) / R;         // rows with ka = 0: t = 0 .. NB/2
+    static constexpr int grid_p3 = n_regular + n_special;
+};
+
+// ------------------------------------------------------------------------------- P1 --
+template <class F, bool PADDED>
+__global__ void __launch_bounds__(kFastThreads, 3) k3_p1(FftParams p) {
+    extern __shared__ __align__(16) float2 sm[];
+    constexpr int LOGC = F::LOGC1_v, C = 1 << LOGC, HALF = C / 2, NA = F::NA_v;
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x << LOGC;
+    const ColLayoutCt<LOGC> lay;
+#pragma unroll 4
+    for (int e = tid; e < NA * HALF; e += kFastThreads) {
+        const int a = e / HALF, c2 = (e - a * HALF) * 2;
+        const int64_t j = ((int64_t)a << F::LOGNBC_v) + r0 + c2;
+        float4 v;
+        if (!PADDED || 2 * j + 3 < p.n_valid) v = __ldg(reinterpret_cast<const float4*>(p.x) + (j >> 1));
+        else {
+            v.x = 2 * j < p.n_valid ? __ldg(p.x + 2 * j) : 0.f;
+            v.y = 2 * j + 1 < p.n_valid ? __ldg(p.x + 2 * j + 1) : 0.f;
+            v.z = 2 * j + 2 < p.n_valid ? __ldg(p.x + 2 * j + 2) : 0.f;
+            v.w = 0.f;
+        }
+        *reinterpret_cast<float4*>(&sm[lay(c2, a)]) = v;
+    }
+    __syncthreads();
+    fft_fwd_ct<F::LOGNA_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGTAB_v>(sm, lay, p.twB, tid);
+#pragma unroll 4
+    for (int e = tid; e < NA * HALF; e += kFastThreads) {
+        const int rho = e / HALF, c2 = (e - rho * HALF) * 2;
+        const int ka = digit_rev_ct<F::LOGNA_v>(rho);
+        const int r = r0 + c2;
+        const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, rho)]);
+        const float2 a = cmul(make_float2(sv.x, sv.y), twiddle_n(p, 2 * (int64_t)ka * r));        // W_M^(ka r) = W_N^(2 ka r)
+        const float2 b = cmul(make_float2(sv.z, sv.w), twiddle_n(p, 2 * (int64_t)ka * (r + 1)));
+        reinterpret_cast<float4*>(p.T)[(((int64_t)ka << F::LOGNBC_v) + r) >> 1] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+
+// --------------------------------------------------------------------------- P2 / P4 --
+template <class F, int DIR>
+__global__ void __launch_bounds__(kFastThreads, 3) k3_p24(FftParams p) {
+    extern __shared__ __align__(16) float2 sm[];
+    constexpr int LOGC = F::LOGC2_v, C = 1 << LOGC, HALF = C / 2, NB = F::NB_v;
+    const int tid = threadIdx.x;
+    const int ka = blockIdx.x >> (F::LOGNC_v - LOGC);
+    const int c0 = (blockIdx.x & ((1 << (F::LOGNC_v - LOGC)) - 1)) << LOGC;
+    const int64_t base = ((int64_t)ka << F::LOGNBC_v) + c0;
+    const ColLayoutCt<LOGC> lay;
+    float4* T4 = reinterpret_cast<float4*>(p.T);
+#pragma unroll 4
+    for (int e = tid; e < NB * HALF; e += kFastThreads) {
+        const int i = e / HALF, c2 = (e - i * HALF) * 2;   // forward: i = b ; inverse: i = kb
+        const int pos = DIR > 0 ? i : digit_pos_ct<F::LOGNB_v>(i);
+        *reinterpret_cast<float4*>(&sm[lay(c2, pos)]) = T4[(base + ((int64_t)i << F::LOGNC_v) + c2) >> 1];
+    }
+    __syncthreads();
+    if (DIR > 0) fft_fwd_ct<F::LOGNB_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGTAB_v>(sm, lay, p.twB, tid);
+    else fft_inv_ct<F::LOGNB_v, CtPlan<F::LOGNB_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGTAB_v>(sm, lay, p.twB, tid);
+#pragma unroll 4
+    for (int e = tid; e < NB * HALF; e += kFastThreads) {
+        const int pos = e / HALF, c2 = (e - pos * HALF) * 2;
+        const int c = c0 + c2;
+        const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, pos)]);
+        float2 a, b;
+        int i;
+        if (DIR > 0) {   // position pos holds kb; stage-2 twiddle W_M'^(kb c) = W_N^(2 NA kb c)
+            i = digit_rev_ct<F::LOGNB_v>(pos);
+            a = cmul(make_float2(sv.x, sv.y), twiddle_n(p, ((int64_t)i * c) << (F::LOGNA_v + 1)));
+            b = cmul(make_float2(sv.z, sv.w), twiddle_n(p, ((int64_t)i * (c + 1)) << (F::LOGNA_v + 1)));
+        } else {         // position pos holds b; undo the stage-1 twiddle W_M^(ka r), r = b NC + c
+            i = pos;
+            const int64_t r = ((int64_t)i << F::LOGNC_v) + c;
+            a = cmul(make_float2(sv.x, sv.y), cconj(twiddle_n(p, 2 * (int64_t)ka * r)));
+            b = cmul(make_float2(sv.z, sv.w), cconj(twiddle_n(p, 2 * (int64_t)ka * (r + 1))));
+        }
+        T4[(base + ((int64_t)i << F::LOGNC_v) + c2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+
+// ------------------------------------------------------------------------------- P3 --
+template <class F>
+__global__ void __launch_bounds__(kFastThreads, 3) k3_p3(FftParams p) {
+    extern __shared__ __align__(16) float2 sm[];
+    constexpr int NA = F::NA_v, NB = F::NB_v, NC = F::NC_v, R = F::R_v, LOGNC = F::LOGNC_v, LOGNB = F::LOGNB_v, LOGNA = F::LOGNA_v;
+    const int tid = threadIdx.x;
+    const bool special = (int)blockIdx.x >= F::n_regular_v;
+    const int t0 = (special ? (int)blockIdx.x - F::n_regular_v : (int)blockIdx.x) * R;
+    const RowLayoutCt lay{F::kRowStride_v};
+    float4* T4 = reinterpret_cast<float4*>(p.T);
+    // slot s in [0, R): rows (rowA, rowB); smem row s holds rowA, smem row R + s holds rowB
+    auto rowA_of = [&](int s) { return special ? t0 + s : NB + t0 + s; };
+    auto rowB_of = [&](int s) { return special ? ((NB - (t0 + s)) & (NB - 1)) : NA * NB - 1 - (t0 + s); };
+    auto valid = [&](int s) { return !special || t0 + s <= NB / 2; };
+    for (int e = tid; e < 2 * R * (NC / 2); e += kFastThreads) {
+        const int srow = e / (NC / 2), i2 = (e - srow * (NC / 2)) * 2;
+        const int s = srow & (R - 1);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid(s)) {
+            const int row = srow < R ? rowA_of(s) : rowB_of(s);
+            v = T4[(((int64_t)row << LOGNC) + i2) >> 1];
+        }
+        sm[lay(srow, i2)] = make_float2(v.x, v.y);
+        sm[lay(srow, i2 + 1)] = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+    fft_fwd_ct<LOGNC, 0, false, F::LOGR_v + 1, RowLayoutCt, F::LOGTAB_v>(sm, lay, p.twB, tid);
+    const float sc = 0.5f * p.inv_scale;
+    for (int e = tid; e < R * NC; e += kFastThreads) {
+        const int s = e >> LOGNC, kc = e & (NC - 1);
+        if (!valid(s)) continue;
+        const int rowA = rowA_of(s), rowB = rowB_of(s);
+        const int ka = rowA >> LOGNB, kb = rowA & (NB - 1);
+        const int64_t k = (int64_t)ka + ((int64_t)kb << LOGNA) + ((int64_t)kc << (LOGNA + LOGNB));
+        const int posk = digit_pos_ct<LOGNC>(kc);
+        if (rowA != rowB) {
+            mid_pair(p, sm[lay(s, posk)], sm[lay(R + s, digit_pos_ct<LOGNC>(NC - 1 - kc))], k, sc);
+        } else if (rowA == 0) {       // (0,0,kc) <-> (0,0,(NC-kc) mod NC)
+            if (kc > NC / 2) continue;
+            if (kc == 0) {
+                const float2 z = sm[lay(s, posk)];
+                const float P0 = (z.x + z.y) * (z.x + z.y), PM = (z.x - z.y) * (z.x - z.y);
+                sm[lay(s, posk)] = make_float2((P0 + PM) * sc, (P0 - PM) * sc);
+            } else {
+                const int pos2 = digit_pos_ct<LOGNC>(NC - kc);
+                float2 a = sm[lay(s, posk)], b = sm[lay(s, pos2)];
+                mid_pair(p, a, b, k, sc);
+                sm[lay(s, posk)] = a;
+                if (pos2 != posk) sm[lay(s, pos2)] = b;
+            }
+        } else {                      // row (0, NB/2): kc <-> NC-1-kc inside the row
+            if (kc >= NC / 2) continue;
+            mid_pair(p, sm[lay(s, posk)], sm[lay(s, digit_pos_ct<LOGNC>(NC - 1 - kc))], k, sc);
+        }
+    }
+    __syncthreads();
+    fft_inv_ct<LOGNC, CtPlan<LOGNC>::nst - 1, false, F::LOGR_v + 1, RowLayoutCt, F::LOGTAB_v>(sm, lay, p.twB, tid);
+    // undo the stage-2 twiddle W_M'^(kb c) and write the rows back in place
+    for (int e = tid; e < 2 * R * (NC / 2); e += kFastThreads) {
+        const int srow = e / (NC / 2), c2 = (e - srow * (NC / 2)) * 2;
+        const int s = srow & (R - 1);
+        if (!valid(s)) continue;
+        const int rowA = rowA_of(s), rowB = rowB_of(s);
+        if (srow >= R && rowA == rowB) continue;
+        const int row = srow < R ? rowA : rowB;
+        const int kb = row & (NB - 1);
+        const float2 a = cmul(sm[lay(srow, c2)], cconj(twiddle_n(p, ((int64_t)kb * c2) << (LOGNA + 1))));
+        const float2 b = cmul(sm[lay(srow, c2 + 1)], cconj(twiddle_n(p, ((int64_t)kb * (c2 + 1)) << (LOGNA + 1))));
+        T4[(((int64_t)row << LOGNC) + c2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+
+// ------------------------------------------------------------------------------- P5 --
+template <class F>
+__global__ void __launch_bounds__(kFastThreads, 3) k3_p5(FftParams p) {
+    extern __shared__ __align__(16) float2 sm[];
+    constexpr int LOGC = F::LOGC1_v, C = 1 << LOGC, HALF = C / 2, NA = F::NA_v;
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x << LOGC;
+    const ColLayoutCt<LOGC> lay;
+    const float4* T4 = reinterpret_cast<const float4*>(p.T);
+#pragma unroll 4
+    for (int e = tid; e < NA * HALF; e += kFastThreads) {
+        const int ka = e / HALF, c2 = (e - ka * HALF) * 2;
+        *reinterpret_cast<float4*>(&sm[lay(c2, digit_pos_ct<F::LOGNA_v>(ka))]) = T4[(((int64_t)ka << F::LOGNBC_v) + r0 + c2) >> 1];
+    }
+    __syncthreads();
+    fft_inv_ct<F::LOGNA_v, CtPlan<F::LOGNA_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGTAB_v>(sm, lay, p.twB, tid);
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+#pragma unroll 4
+    for (int e = tid; e < NA * HALF; e += kFastThreads) {
+        const int a = e / HALF, c2 = (e - a * HALF) * 2;
+        const int64_t j = ((int64_t)a << F::LOGNBC_v) + r0 + c2;
+        const int64_t m0 = 2 * j;   // y[j] = r[2j] + i r[2j+1]: two adjacent columns = four consecutive lags
+        if (m0 > p.m_hi || m0 + 3 < p.m_lo) continue;
+        const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, a)]);
+        float o[4] = {sv.x, sv.y, sv.z, sv.w};
+        if (!p.raw) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                o[t] = o[t] * o[t];  // abs2 of the (real) correlation
+                if (p.log_scale) o[t] = 10.0f * log10f(o[t]);
+            }
+        }
+        if (out_aligned && m0 >= p.m_lo && m0 + 3 <= p.m_hi && (((m0 - p.m_lo) & 3) == 0)) {
+            *reinterpret_cast<float4*>(p.out + (m0 - p.m_lo)) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (m0 + t >= p.m_lo && m0 + t <= p.m_hi) p.out[m0 + t - p.m_lo] = o[t];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------- dispatch --
+struct Fft3Kernels {
+    void (*p1)(FftParams);
+    void (*p1_padded)(FftParams);
+    void (*p2)(FftParams);
+    void (*p3)(FftParams);
+    void (*p4)(FftParams);
+    void (*p5)(FftParams);
+    int grid_p1, grid_p2, grid_p3;
+    size_t smem_p1, smem_p2, smem_p3;
+};
+
+// the kernels take the shape through a traits class with plain static members
+template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB>
+struct Fft3Traits {
+    using G = Fft3<LOGNA, LOGNB, LOGNC, LOGC1, LOGC2, LOGR, LOGTAB>;
+    static constexpr int LOGNA_v = LOGNA, LOGNB_v = LOGNB, LOGNC_v = LOGNC, LOGC1_v = LOGC1, LOGC2_v = LOGC2, LOGR_v = LOGR,
+                         LOGTAB_v = LOGTAB, LOGNBC_v = LOGNB + LOGNC, NA_v = 1 << LOGNA, NB_v = 1 << LOGNB, NC_v = 1 << LOGNC,
+                         R_v = 1 << LOGR, kRowStride_v = G::kRowStride, n_regular_v = G::n_regular;
+};
+
+template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB>
+static Fft3Kernels make_fft3() {
+    using F = Fft3Traits<LOGNA, LOGNB, LOGNC, LOGC1, LOGC2, LOGR, LOGTAB>;
+    using G = typename F::G;
+    Fft3Kernels k;
+    k.p1 = k3_p1<F, false>; k.p1_padded = k3_p1<F, true>;
+    k.p2 = k3_p24<F, +1>; k.p4 = k3_p24<F, -1>;
+    k.p3 = k3_p3<F>; k.p5 = k3_p5<F>;
+    k.grid_p1 = G::grid_p1; k.grid_p2 = G::grid_p2; k.grid_p3 = G::grid_p3;
+    k.smem_p1 = G::smem_p1; k.smem_p2 = G::smem_p2; k.smem_p3 = G::smem_p3;
+    return k;
+}
+
+// shapes with a three-level build, keyed by log2 of the transform length N (real samples) and of
+// the two-level B table length (the W_B^k table the plan already owns, reused with a stride)
+static bool find_fft3(int logN, int logtab, Fft3Kernels* out) {
+#define TSDR_FFT3(n, a, b, c, c1, c2, r, tab) if (logN == n && logtab == tab) { *out = make_fft3<a, b, c, c1, c2, r, tab>(); return true; }
+    TSDR_FFT3(22, 7, 7, 7, 5, 5, 5, 12)   // M = 2^21
+    TSDR_FFT3(23, 8, 7, 7, 5, 5, 5, 12)   // M = 2^22 (the GUI's 3e6 / 4e6 samples after zero padding)
+    TSDR_FFT3(24, 8, 8, 7, 5, 5, 5, 12)   // M = 2^23: the benchmark size
+    TSDR_FFT3(25, 8, 8, 8, 5, 5, 4, 13)   // M = 2^24
+    TSDR_FFT3(26, 9, 8, 8, 4, 5, 4, 13)   // M = 2^25
+#undef TSDR_FFT3
+    return false;
+}
+
+}  // namespace tsdr

@@ -259,6 +259,8 @@ def _periodic_power(n, period, seed):
     (3000, 3000.0, 0.5),             # not a power of two: zero-pad + fold path
     (30000, 20000.0, 0.6),           # n = min(2*indexMax, len) = 24000
     (100, 1000.0, 0.05),             # tiny
+    (1 << 22, float(1 << 22), 0.5),  # three-level kernels, direct circular transform
+    (3_000_000, 20e6, 0.075),        # the GUI's length with acquisition = 0.05 s: zero-padded to N = 2^23, three-level + fold
 ])
 def test_autocorr_matches_oracle(n, Fs, maxDelay):
     x = _periodic_power(n, 37 if n < 5000 else 1234, n)
