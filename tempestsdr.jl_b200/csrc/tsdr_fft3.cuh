@@ -26,7 +26,8 @@ struct Fft3 {
     static constexpr int NA = 1 << LOGNA, NB = 1 << LOGNB, NC = 1 << LOGNC;
     static constexpr int LOGNBC = LOGNB + LOGNC;
     static constexpr int R = 1 << LOGR;
-    static constexpr int kRowStride = NC + (NC >> 4) + 1;
+    // padded row length with stride = 8 (mod 16) elements: two rows then cover all 32 banks in the radix-16 stage
+    static constexpr int kRowStride = ((NC + (NC >> 4)) & 15) == 8 ? NC + (NC >> 4) : ((NC + (NC >> 4) + 15) & ~15) + 8;
     static constexpr size_t smem_p1 = (size_t)col_padded_ct<LOGC1>(NA << LOGC1) * sizeof(float2);
     static constexpr size_t smem_p2 = (size_t)col_padded_ct<LOGC2>(NB << LOGC2) * sizeof(float2);
     static constexpr size_t smem_p3 = (size_t)2 * R * kRowStride * sizeof(float2);
@@ -37,15 +38,24 @@ struct Fft3 {
     static constexpr int grid_p3 = n_regular + n_special;
 };
 
+// W_len^k, k in [0, len), copied from the plan's longer table into shared memory: the butterflies'
+// twiddle reads then are LDS instead of global loads in the middle of every dependent chain
+template <int LOGLEN, int LOGTAB>
+__device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* __restrict__ tab, int tid) {
+    for (int k = tid; k < (1 << LOGLEN); k += kFastThreads) tw_s[k] = __ldg(tab + ((size_t)k << (LOGTAB - LOGLEN)));
+}
+
 // ------------------------------------------------------------------------------- P1 --
 template <class F, bool PADDED>
 __global__ void __launch_bounds__(kFastThreads, 3) k3_p1(FftParams p) {
     extern __shared__ __align__(16) float2 sm[];
     constexpr int LOGC = F::LOGC1_v, C = 1 << LOGC, HALF = C / 2, NA = F::NA_v;
+    __shared__ float2 tw_s[NA];
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x << LOGC;
     const ColLayoutCt<LOGC> lay;
-#pragma unroll 4
+    load_twiddles<F::LOGNA_v, F::LOGTAB_v>(tw_s, p.twB, tid);
+#pragma unroll
     for (int e = tid; e < NA * HALF; e += kFastThreads) {
         const int a = e / HALF, c2 = (e - a * HALF) * 2;
         const int64_t j = ((int64_t)a << F::LOGNBC_v) + r0 + c2;
@@ -60,7 +70,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p1(FftParams p) {
         *reinterpret_cast<float4*>(&sm[lay(c2, a)]) = v;
     }
     __syncthreads();
-    fft_fwd_ct<F::LOGNA_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGTAB_v>(sm, lay, p.twB, tid);
+    fft_fwd_ct<F::LOGNA_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGNA_v>(sm, lay, tw_s, tid);
 #pragma unroll 4
     for (int e = tid; e < NA * HALF; e += kFastThreads) {
         const int rho = e / HALF, c2 = (e - rho * HALF) * 2;
@@ -84,15 +94,17 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p24(FftParams p) {
     const int64_t base = ((int64_t)ka << F::LOGNBC_v) + c0;
     const ColLayoutCt<LOGC> lay;
     float4* T4 = reinterpret_cast<float4*>(p.T);
-#pragma unroll 4
+    __shared__ float2 tw_s[NB];
+    load_twiddles<F::LOGNB_v, F::LOGTAB_v>(tw_s, p.twB, tid);
+#pragma unroll
     for (int e = tid; e < NB * HALF; e += kFastThreads) {
         const int i = e / HALF, c2 = (e - i * HALF) * 2;   // forward: i = b ; inverse: i = kb
         const int pos = DIR > 0 ? i : digit_pos_ct<F::LOGNB_v>(i);
         *reinterpret_cast<float4*>(&sm[lay(c2, pos)]) = T4[(base + ((int64_t)i << F::LOGNC_v) + c2) >> 1];
     }
     __syncthreads();
-    if (DIR > 0) fft_fwd_ct<F::LOGNB_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGTAB_v>(sm, lay, p.twB, tid);
-    else fft_inv_ct<F::LOGNB_v, CtPlan<F::LOGNB_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGTAB_v>(sm, lay, p.twB, tid);
+    if (DIR > 0) fft_fwd_ct<F::LOGNB_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGNB_v>(sm, lay, tw_s, tid);
+    else fft_inv_ct<F::LOGNB_v, CtPlan<F::LOGNB_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGNB_v>(sm, lay, tw_s, tid);
 #pragma unroll 4
     for (int e = tid; e < NB * HALF; e += kFastThreads) {
         const int pos = e / HALF, c2 = (e - pos * HALF) * 2;
@@ -124,10 +136,13 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p3(FftParams p) {
     const int t0 = (special ? (int)blockIdx.x - F::n_regular_v : (int)blockIdx.x) * R;
     const RowLayoutCt lay{F::kRowStride_v};
     float4* T4 = reinterpret_cast<float4*>(p.T);
+    __shared__ float2 tw_s[NC];
+    load_twiddles<LOGNC, F::LOGTAB_v>(tw_s, p.twB, tid);
     // slot s in [0, R): rows (rowA, rowB); smem row s holds rowA, smem row R + s holds rowB
     auto rowA_of = [&](int s) { return special ? t0 + s : NB + t0 + s; };
     auto rowB_of = [&](int s) { return special ? ((NB - (t0 + s)) & (NB - 1)) : NA * NB - 1 - (t0 + s); };
     auto valid = [&](int s) { return !special || t0 + s <= NB / 2; };
+#pragma unroll
     for (int e = tid; e < 2 * R * (NC / 2); e += kFastThreads) {
         const int srow = e / (NC / 2), i2 = (e - srow * (NC / 2)) * 2;
         const int s = srow & (R - 1);
@@ -140,7 +155,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p3(FftParams p) {
         sm[lay(srow, i2 + 1)] = make_float2(v.z, v.w);
     }
     __syncthreads();
-    fft_fwd_ct<LOGNC, 0, false, F::LOGR_v + 1, RowLayoutCt, F::LOGTAB_v>(sm, lay, p.twB, tid);
+    fft_fwd_ct<LOGNC, 0, false, F::LOGR_v + 1, RowLayoutCt, LOGNC>(sm, lay, tw_s, tid);
     const float sc = 0.5f * p.inv_scale;
     for (int e = tid; e < R * NC; e += kFastThreads) {
         const int s = e >> LOGNC, kc = e & (NC - 1);
@@ -170,7 +185,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p3(FftParams p) {
         }
     }
     __syncthreads();
-    fft_inv_ct<LOGNC, CtPlan<LOGNC>::nst - 1, false, F::LOGR_v + 1, RowLayoutCt, F::LOGTAB_v>(sm, lay, p.twB, tid);
+    fft_inv_ct<LOGNC, CtPlan<LOGNC>::nst - 1, false, F::LOGR_v + 1, RowLayoutCt, LOGNC>(sm, lay, tw_s, tid);
     // undo the stage-2 twiddle W_M'^(kb c) and write the rows back in place
     for (int e = tid; e < 2 * R * (NC / 2); e += kFastThreads) {
         const int srow = e / (NC / 2), c2 = (e - srow * (NC / 2)) * 2;
@@ -195,13 +210,15 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p5(FftParams p) {
     const int r0 = blockIdx.x << LOGC;
     const ColLayoutCt<LOGC> lay;
     const float4* T4 = reinterpret_cast<const float4*>(p.T);
-#pragma unroll 4
+    __shared__ float2 tw_s[NA];
+    load_twiddles<F::LOGNA_v, F::LOGTAB_v>(tw_s, p.twB, tid);
+#pragma unroll
     for (int e = tid; e < NA * HALF; e += kFastThreads) {
         const int ka = e / HALF, c2 = (e - ka * HALF) * 2;
         *reinterpret_cast<float4*>(&sm[lay(c2, digit_pos_ct<F::LOGNA_v>(ka))]) = T4[(((int64_t)ka << F::LOGNBC_v) + r0 + c2) >> 1];
     }
     __syncthreads();
-    fft_inv_ct<F::LOGNA_v, CtPlan<F::LOGNA_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGTAB_v>(sm, lay, p.twB, tid);
+    fft_inv_ct<F::LOGNA_v, CtPlan<F::LOGNA_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGNA_v>(sm, lay, tw_s, tid);
     const bool out_aligned = (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
 #pragma unroll 4
     for (int e = tid; e < NA * HALF; e += kFastThreads) {
