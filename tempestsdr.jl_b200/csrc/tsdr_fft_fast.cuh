@@ -83,7 +83,7 @@ __device__ __forceinline__ void stage_ct(float2* s, const Layout lay, const floa
         if (LOGSUB > 0) {
             const int ub = u << TWSHIFT;
 #pragma unroll
-            for (int p = 1; p < R; ++p) if (p < 4 || (p & 3) == 0) wv[p] = __ldg(tw + ub * p);
+            for (int p = 1; p < R; ++p) if (p < 4 || (p & 3) == 0) wv[p] = tw[ub * p];  // plain load: the table may live in shared memory
 #pragma unroll
             for (int p = 5; p < R; ++p) if ((p & 3) != 0) wv[p] = cmul(wv[p & ~3], wv[p & 3]);
         }
