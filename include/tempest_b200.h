@@ -91,6 +91,9 @@ int tsdr_autocorr_out_len(size_t len, double Fs, double min_delay, double max_de
 /* first-maximum search, Base.findmax semantics (NaN dominates); 1-based index.
  * Used for the refresh/line peak picks  src/GUI.jl:79, production/investigate_data.jl:60,80 */
 int tsdr_findmax_f32(const float* v, size_t n, float* value, size_t* index1);
+/* same on a DEVICE vector (windowed peak picks on a device-resident Gamma: pass v_dev + offset, window length);
+ * stream: the cudaStream_t the vector was produced on (NULL = default stream) */
+int tsdr_findmax_dev_f32(const float* v_dev, size_t n, float* value, size_t* index1, void* stream);
 
 /* fullScale!(mat) = (mat .- min)/(max - min)     src/ScreenRenderer.jl:35-39 */
 int tsdr_full_scale_f32(const float* in, float* out, size_t n);

@@ -17,7 +17,7 @@ from .video_configurations import (VideoMode, allVideoConfigurations, find_close
 
 __all__ = [
     "amDemod", "invert_amDemod", "fmDemod", "abs2", "sig_to_image", "downgradeImage", "naiveResampler", "init_resampler",
-    "calculate_autocorrelation", "zoom_autocorr", "findmax", "SyncXY", "vsync", "fullScale",
+    "calculate_autocorrelation", "zoom_autocorr", "findmax", "findmax_device", "sweep_refresh_hypotheses", "SyncXY", "vsync", "fullScale",
     "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
     "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
     "Chain", "AutocorrPlan", "extract_configuration", "estimate_lines", "TempestError", "RENDERING_SIZE",
@@ -167,6 +167,14 @@ def findmax(v):
     a = np.ascontiguousarray(v, dtype=np.float32)
     val, idx = C.c_float(0), C.c_size_t(0)
     check(_lib.load().tsdr_findmax_f32(_ptr(a), a.size, C.byref(val), C.byref(idx)))
+    return np.float32(val.value), idx.value
+
+
+def findmax_device(ptr, n, stream=None):
+    """findmax over n floats at device pointer `ptr` -> (value, 1-based index)"""
+    val, idx = C.c_float(0), C.c_size_t(0)
+    check(_lib.load().tsdr_findmax_dev_f32(C.c_void_p(ptr), int(n), C.byref(val), C.byref(idx),
+                                           C.c_void_p(stream) if stream else None))
     return np.float32(val.value), idx.value
 
 
@@ -408,6 +416,28 @@ def extract_configuration(sig_corr, Fs, delayRate=1 / 10, rate_min=50, rate_max=
     posMax_time = 1 / rates_refresh[posMax - 1]
     fv = 1 / posMax_time
     return rates_refresh, Gamma_refresh, fv
+
+
+def sweep_refresh_hypotheses(gamma_ptr, n_gamma, Fs, hypotheses=None, half_width_hz=0.5, stream=None, rank=0, world=1):
+    """BASELINE cfg 4: score every refresh-rate hypothesis of allVideoConfigurations against a DEVICE-resident
+    Gamma (output of AutocorrPlan.exec with index_min = 1).  For refresh rate r the window is the
+    zoom_autocorr window [r - hw, r + hw] (same index convention as src/Autocorrelations.jl:42-53); the score is the
+    window's first maximum (findmax on the GPU).  Hypotheses are sharded round-robin over `world` ranks (no exchange
+    needed on the data path; gather the small result lists on the host).  Returns [(rate, score_dB, fv_hat, lag_index)]."""
+    if hypotheses is None:
+        hypotheses = sorted(get_refresh_rates(allVideoConfigurations))
+    out = []
+    for i, r in enumerate(hypotheses):
+        if i % world != rank:
+            continue
+        lo = min(_round(1 / (r + half_width_hz) * Fs), n_gamma)
+        hi = min(_round(1 / (r - half_width_hz) * Fs), n_gamma)
+        if hi < lo or lo < 1:
+            continue
+        val, idx = findmax_device(gamma_ptr + 4 * (lo - 1), hi - lo + 1, stream)
+        k = lo + idx - 1                      # 1-based index into Gamma; the reference reads it as lag k/Fs
+        out.append((float(r), float(val), 1.0 / (k / Fs), int(k)))
+    return out
 
 
 def estimate_lines(Gamma, Fs, fv, N=500):

@@ -388,6 +388,29 @@ int tsdr_findmax_f32(const float* v, size_t n, float* value, size_t* index1) {
     return TSDR_OK;
 }
 
+/* windowed first-maximum search on a DEVICE vector (K6): v_dev[0..n), 1-based index of the first maximum */
+int tsdr_findmax_dev_f32(const float* v_dev, size_t n, float* value, size_t* index1, void* stream) {
+    TSDR_REQUIRE(v_dev && n > 0, "findmax of an empty collection");
+    TSDR_REQUIRE(n < 0xffffffffull, "vector too long");
+    int rc = ensure_device(); if (rc) return rc;
+    void* d_part;
+    const int parts = 512;
+    if ((rc = scratch(2, parts * 8 + 16, &d_part))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = (int)std::min<size_t>(parts, ew_blocks(n));
+    k_findmax_partial<<<nb, kEwThreads, 0, st>>>(v_dev, n, (unsigned long long*)d_part);
+    TSDR_CUDA(cudaGetLastError());
+    unsigned long long h[512];
+    TSDR_CUDA(cudaMemcpyAsync(h, d_part, nb * 8, cudaMemcpyDeviceToHost, st));
+    TSDR_CUDA(cudaStreamSynchronize(st));
+    unsigned long long best = 0;
+    for (int i = 0; i < nb; ++i) best = h[i] > best ? h[i] : best;
+    const size_t idx = (size_t)(0xffffffffu - (unsigned int)(best & 0xffffffffull));
+    if (value) TSDR_CUDA(cudaMemcpy(value, v_dev + idx, sizeof(float), cudaMemcpyDeviceToHost));
+    if (index1) *index1 = idx + 1;
+    return TSDR_OK;
+}
+
 // ------------------------------------------------------------- SyncXY ------
 }  // extern "C"
 

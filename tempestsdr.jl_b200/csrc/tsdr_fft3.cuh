@@ -283,10 +283,9 @@ static Fft3Kernels make_fft3() {
 // the two-level B table length (the W_B^k table the plan already owns, reused with a stride)
 static bool find_fft3(int logN, int logtab, Fft3Kernels* out) {
 #define TSDR_FFT3(n, a, b, c, c1, c2, r, tab) if (logN == n && logtab == tab) { *out = make_fft3<a, b, c, c1, c2, r, tab>(); return true; }
-    TSDR_FFT3(22, 7, 7, 7, 5, 5, 5, 12)   // M = 2^21
-    TSDR_FFT3(23, 8, 7, 7, 5, 5, 5, 12)   // M = 2^22 (the GUI's 3e6 / 4e6 samples after zero padding)
+    // measured on B200 (tools/run_autocorr.py): the three-level split wins at 2^24 (0.283 vs 0.306 ms) and
+    // 2^26 (1.35 vs 1.47 ms); at 2^22, 2^23 and 2^25 the two-level kernels are a few percent faster.
     TSDR_FFT3(24, 8, 8, 7, 5, 5, 5, 12)   // M = 2^23: the benchmark size
-    TSDR_FFT3(25, 8, 8, 8, 5, 5, 4, 13)   // M = 2^24
     TSDR_FFT3(26, 9, 8, 8, 4, 5, 4, 13)   // M = 2^25
 #undef TSDR_FFT3
     return false;

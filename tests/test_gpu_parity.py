@@ -400,3 +400,78 @@ def test_gpu_matches_committed_goldens():
     ch.close()
     got, _ = tsdr.calculate_autocorrelation(G["autocorr_in"], 6000.0, 0, 0.5)
     assert np.max(np.abs(got - G["autocorr_db"])) <= 1e-2
+
+
+def test_findmax_device_and_hypothesis_sweep(synth):
+    import torch
+    Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)
+    iq = synth.make_iq(int(0.25 * Fs), Fs, x_t, y_t, fv, seed=21)
+    power = orc.abs2(iq)
+    n = 1 << 18
+    x = torch.from_numpy(power[:n].copy()).cuda()
+    L = n // 2
+    out = torch.empty(L, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        plan = tsdr.AutocorrPlan(n, stream=s.cuda_stream)
+        plan.exec(x.data_ptr(), 1, L, out.data_ptr())
+    s.synchronize()
+    g = out.cpu().numpy()
+    val, idx = tsdr.findmax_device(out.data_ptr() + 4 * 1000, 5000, s.cuda_stream)
+    rv, ri = orc.findmax(g[1000:6000])
+    assert (val, idx) == (rv, ri)
+    res = tsdr.sweep_refresh_hypotheses(out.data_ptr(), L, Fs, stream=s.cuda_stream)
+    ref = []
+    for r in sorted(tsdr.get_refresh_rates(tsdr.allVideoConfigurations)):
+        rates, sl = orc.zoom_autocorr(g, Fs, rate_min=r - 0.5, rate_max=r + 0.5)
+        v, i = orc.findmax(sl)
+        ref.append((float(r), float(v), float(rates[i - 1])))
+    assert [(a, b, c) for a, b, c, _ in res] == ref
+    best = max(res, key=lambda t: t[1])
+    assert best[0] == 60.0                       # the synthetic capture is a 60 Hz mode
+    halves = tsdr.sweep_refresh_hypotheses(out.data_ptr(), L, Fs, stream=s.cuda_stream, rank=0, world=2) + \
+        tsdr.sweep_refresh_hypotheses(out.data_ptr(), L, Fs, stream=s.cuda_stream, rank=1, world=2)
+    assert sorted(halves) == sorted(res)
+    plan.close()
+
+
+def test_chain_largest_mode_cfg5_shape(synth):
+    # BASELINE cfg 5 shape: 3840x2160@30 (CTA-861 total raster 4400x2250) at 200 MS/s, two frames
+    Fs, (x_t, y_t, fv), alpha = 200e6, (4400, 2250, 30.0), 0.1
+    S = orc.frame_samples(Fs, fv)
+    assert S == 6666667
+    iq = synth.make_iq(2 * S + 1, Fs, x_t, y_t, fv, seed=55)
+    ref, _, sy_ref, sx_ref = orc.chain_buffer(iq, Fs, x_t, y_t, fv, alpha, orc.SyncXY(), np.zeros((600, 800), np.float32),
+                                              publish=False, nthreads=4)
+    ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=alpha, max_samples=iq.size)
+    assert ch.push(iq) == 2
+    sy, sx = ch.offsets()
+    assert np.array_equal(sy, sy_ref) and np.array_equal(sx, sx_ref)
+    assert np.array_equal(ch.image(), ref)
+    ch.close()
+
+
+def test_chain_with_nan_and_extreme_samples(synth):
+    # NaN / inf / tiny / huge samples must travel through envelope, resize, projections, beta and findmax like the oracle
+    Fs, (x_t, y_t, fv), alpha = 2.0e6, (1056, 628, 60.0), 0.1
+    S = orc.frame_samples(Fs, fv)
+    iq = synth.make_iq(3 * S, Fs, x_t, y_t, fv, seed=66)
+    iq[S + 1234] = np.nan
+    iq[S + 20000] = np.inf + 1j
+    iq[100] = 1e-30 + 1e-31j
+    iq[200] = 3e30 - 2e30j
+    iq[2 * S + 5] = 0
+    so = orc.SyncXY()
+    ref, fr_ref, sy_ref, sx_ref = orc.chain_buffer(iq, Fs, x_t, y_t, fv, alpha, so, np.zeros((600, 800), np.float32))
+    ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=alpha, max_samples=iq.size, publish_all=True)
+    assert ch.push(iq) == 3
+    sy, sx = ch.offsets()
+    assert np.array_equal(sy, sy_ref) and np.array_equal(sx, sx_ref)
+    got = ch.image()
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
+    pub = ch.published()
+    for f in range(3):
+        m = ~np.isnan(fr_ref[f])
+        assert np.array_equal(np.isnan(pub[f]), ~m) and np.array_equal(pub[f][m], fr_ref[f][m])
+    ch.close()
