@@ -309,6 +309,15 @@ class Chain:
         check(_lib.load().tsdr_chain_push_host(self._h, C.c_void_p(ptr), int(n), C.byref(nf)))
         return nf.value
 
+    def push_deliver_ptr(self, iq_ptr, n, image_out_ptr):
+        """push a (pinned) host buffer and deliver this buffer's imageOut asynchronously to a (pinned) host image"""
+        nf = C.c_int(0)
+        check(_lib.load().tsdr_chain_push_host_deliver(self._h, C.c_void_p(iq_ptr), int(n), C.byref(nf), C.c_void_p(image_out_ptr)))
+        return nf.value
+
+    def wait_delivery(self, age=0):
+        check(_lib.load().tsdr_chain_wait_delivery(self._h, int(age)))
+
     def push_device(self, ptr, n):
         nf = C.c_int(0)
         check(_lib.load().tsdr_chain_push_device(self._h, C.c_void_p(ptr), int(n), C.byref(nf)))

@@ -475,3 +475,25 @@ def test_chain_with_nan_and_extreme_samples(synth):
         m = ~np.isnan(fr_ref[f])
         assert np.array_equal(np.isnan(pub[f]), ~m) and np.array_equal(pub[f][m], fr_ref[f][m])
     ch.close()
+
+
+def test_push_deliver_matches_push_plus_image(synth):
+    import torch
+    Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)
+    S = orc.frame_samples(Fs, fv)
+    n = 2 * S + 7
+    bufs = [torch.from_numpy(synth.make_iq(n, Fs, x_t, y_t, fv, seed=90 + b, t0=b * n).view(np.float32).copy()).pin_memory() for b in range(4)]
+    outs = [torch.empty((800, 600), dtype=torch.float32).pin_memory() for _ in range(2)]
+    a = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=0.3, max_samples=n)
+    ref = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=0.3, max_samples=n)
+    for b in range(4):
+        assert a.push_deliver_ptr(bufs[b].data_ptr(), n, outs[b % 2].data_ptr()) == 2
+        if b:
+            a.wait_delivery(1)
+            want_prev = prev
+            assert np.array_equal(outs[(b - 1) % 2].numpy().T, want_prev)
+        ref.push(bufs[b].numpy().view(np.complex64))
+        prev = ref.image().copy()
+    a.wait_delivery(0)
+    assert np.array_equal(outs[3 % 2].numpy().T, prev)
+    a.close(); ref.close()
