@@ -4,7 +4,6 @@
 #include "tsdr_kernels.cuh"
 
 #include <algorithm>
-#include <cstdlib>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -608,9 +607,7 @@ struct tsdr_chain {
     uint64_t launches;
     RenderParams rp;
     SyncParams sp;
-    size_t smem_bytes;       // k_render (windows of G rows)
-    size_t smem_rows_bytes;  // k_render_rows (window of one row)
-    int win_single;
+    size_t smem_bytes;
     // device memory
     float* d_iq2[2];    // two staging buffers for push_host (max_samples + pad each)
     float* d_frames2[2]; // 2 x [max_frames][600][800]: render of buffer b+1 overlaps the sync/accumulate of buffer b
@@ -692,7 +689,6 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         win_lo[i] = (int)flo; win_len[i] = W;
         if (W > win) win = W;
     }
-    const int win_one = win;  // largest single-row window
     // G output rows per CTA: as many as keep the staged window under ~20 KB (small windows are
     // dominated by per-CTA fixed cost); the window of a group is the union of its rows' windows
     int G = 1;
@@ -745,9 +741,6 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
 
     c->Fs = Fs; c->fv = fv; c->x_t = x_t; c->y_t = y_t; c->S = S; c->max_frames = max_frames;
     c->smem_bytes = smem;
-    c->smem_rows_bytes = (size_t)(win_one + 4) * sizeof(double);
-    c->win_single = win_one;
-    TSDR_CUDA(cudaFuncSetAttribute(k_render_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_rows_bytes));
     RenderParams& rp = c->rp;
     rp.S = S; rp.x_t = x_t; rp.y_t = y_t;
     rp.sf1 = m1.sf; rp.off1 = m1.off; rp.clamp1 = m1.clamp; rp.identity1 = m1.identity; rp.identity2 = identity2;
@@ -815,15 +808,8 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     rp.iq = iq_dev; rp.n_ech = (int64_t)n; rp.frames = c->d_frames2[par];
     if (piped) TSDR_CUDA(cudaStreamWaitEvent(st, c->ev_free[par], 0));  // frames[par] released by the push before last
     mark(st);
-    if (!rp.identity1 && !rp.identity2 && c->win_single <= 32000 && !getenv("TSDR_RENDER_PER_FRAME")) {
-        // general case: one CTA per output row, resampling coordinates cached across `fpc` frames
-        const int fpc = nb >= 10 ? 5 : (nb >= 4 ? 2 : 1);
-        dim3 grid(kRenderH, (nb + fpc - 1) / fpc);
-        k_render_rows<<<grid, kRenderThreads, c->smem_rows_bytes, st>>>(rp, nb, fpc);
-    } else {
-        dim3 grid((kRenderH + rp.rows_per_cta - 1) / rp.rows_per_cta, nb);
-        k_render<<<grid, kRenderThreads, c->smem_bytes, st>>>(rp);
-    }
+    dim3 grid((kRenderH + rp.rows_per_cta - 1) / rp.rows_per_cta, nb);
+    k_render<<<grid, kRenderThreads, c->smem_bytes, st>>>(rp);
     c->launches += 1;
     mark(st);
     if (piped) {
