@@ -136,11 +136,19 @@ int tsdr_chain_reset(tsdr_chain* c);
  * copy asynchronous); the device variant reads the caller's buffer in place. */
 int tsdr_chain_push_host(tsdr_chain* c, const float* iq_host, size_t n, int* n_frames);
 int tsdr_chain_push_device(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames);
+/* push_host for a buffer of interleaved Int16 (re, im) samples -- the `:short` recordings that
+ * readComplexBinary (src/DatBinaryFiles.jl:47-49,64) widens to ComplexF32 on the host.  Only 4 bytes per
+ * sample cross PCIe and HBM; the widening (exact, no scaling, as the reference) happens inside the render
+ * kernel.  The device variant needs a 16-byte aligned buffer that is readable up to a whole number of
+ * 4-sample groups (round the allocation up to a multiple of 16 bytes). */
+int tsdr_chain_push_host_i16(tsdr_chain* c, const int16_t* iq_host, size_t n, int* n_frames);
+int tsdr_chain_push_device_i16(tsdr_chain* c, const int16_t* iq_dev, size_t n, int* n_frames);
 /* push_host + asynchronous delivery of THIS buffer's imageOut (600 x 800, column-major) into image_out_host
  * (pinned memory keeps it asynchronous) -- the reference's non_blocking_put!(imageOut) per buffer (GUI.jl:177).
  * Nothing blocks the host: the H2D copy of the next buffer overlaps the kernels and the D2H of this one.
  * tsdr_chain_wait_delivery(c, 0) blocks until the latest delivery has landed, (c, 1) the one before it. */
 int tsdr_chain_push_host_deliver(tsdr_chain* c, const float* iq_host, size_t n, int* n_frames, float* image_out_host);
+int tsdr_chain_push_host_i16_deliver(tsdr_chain* c, const int16_t* iq_host, size_t n, int* n_frames, float* image_out_host);
 int tsdr_chain_wait_delivery(tsdr_chain* c, int age);
 /* Run the frames of a buffer through render + sync search WITHOUT accumulating them: only
  * the SyncXY state (the stale beta_y of FrameSynchronisation.jl:66) advances.  A rank that

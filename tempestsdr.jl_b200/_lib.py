@@ -53,6 +53,9 @@ SIGNATURES = {
     "tsdr_chain_reset": (C.c_int, [_vp]),
     "tsdr_chain_push_host": (C.c_int, [_vp, _vp, C.c_size_t, _ip]),
     "tsdr_chain_push_device": (C.c_int, [_vp, _vp, C.c_size_t, _ip]),
+    "tsdr_chain_push_host_i16": (C.c_int, [_vp, _vp, C.c_size_t, _ip]),
+    "tsdr_chain_push_host_i16_deliver": (C.c_int, [_vp, _vp, C.c_size_t, _ip, _vp]),
+    "tsdr_chain_push_device_i16": (C.c_int, [_vp, _vp, C.c_size_t, _ip]),
     "tsdr_chain_push_host_deliver": (C.c_int, [_vp, _vp, C.c_size_t, _ip, _vp]),
     "tsdr_chain_wait_delivery": (C.c_int, [_vp, C.c_int]),
     "tsdr_chain_prime_host": (C.c_int, [_vp, _vp, C.c_size_t]),

@@ -298,6 +298,17 @@ class Chain:
         self._keep = [z] + list(getattr(self, "_keep", []))[:1]
         return nf.value
 
+    def push_i16(self, iq16):
+        """one buffer of interleaved Int16 (re, im) samples as a `:short` .dat file stores them
+        (src/DatBinaryFiles.jl:47-49): numpy int16 of shape (n, 2) or (2n,)"""
+        z = np.ascontiguousarray(iq16, dtype=np.int16).reshape(-1)
+        if z.size % 2:
+            raise ValueError("Int16 IQ buffer needs an even number of values (re, im pairs)")
+        nf = C.c_int(0)
+        check(_lib.load().tsdr_chain_push_host_i16(self._h, _ptr(z), z.size // 2, C.byref(nf)))
+        self._keep = [z] + list(getattr(self, "_keep", []))[:1]
+        return nf.value
+
     def prime(self, iq):
         """advance only the SyncXY state with these frames (halo frame of a sharded integration)"""
         z, n = _iq(iq)
@@ -315,12 +326,24 @@ class Chain:
         check(_lib.load().tsdr_chain_push_host_deliver(self._h, C.c_void_p(iq_ptr), int(n), C.byref(nf), C.c_void_p(image_out_ptr)))
         return nf.value
 
+    def push_i16_deliver_ptr(self, iq16_ptr, n, image_out_ptr):
+        """push_deliver_ptr for a (pinned) buffer of Int16 (re, im) pairs"""
+        nf = C.c_int(0)
+        check(_lib.load().tsdr_chain_push_host_i16_deliver(self._h, C.c_void_p(iq16_ptr), int(n), C.byref(nf), C.c_void_p(image_out_ptr)))
+        return nf.value
+
     def wait_delivery(self, age=0):
         check(_lib.load().tsdr_chain_wait_delivery(self._h, int(age)))
 
     def push_device(self, ptr, n):
         nf = C.c_int(0)
         check(_lib.load().tsdr_chain_push_device(self._h, C.c_void_p(ptr), int(n), C.byref(nf)))
+        return nf.value
+
+    def push_device_i16(self, ptr, n):
+        """Int16 (re, im) pairs already in device memory: 16-byte aligned, allocation rounded up to 16 bytes"""
+        nf = C.c_int(0)
+        check(_lib.load().tsdr_chain_push_device_i16(self._h, C.c_void_p(ptr), int(n), C.byref(nf)))
         return nf.value
 
     def sync(self):

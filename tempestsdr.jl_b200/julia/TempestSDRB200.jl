@@ -159,6 +159,19 @@ mutable struct Chain
 end
 
 # one recv! buffer: amDemod -> sig_to_image -> downgradeImage -> vsync -> circshift -> EMA for every frame
+# a buffer read from a `:short` recording without the host-side widening of readComplexBinary
+# (src/DatBinaryFiles.jl:47-49): raw = reinterpret(Int16, read(file)) holds (re, im) pairs
+function push_int16!(c::Chain, raw::Vector{Int16})
+    iseven(length(raw)) || throw(ArgumentError("Int16 IQ buffer needs (re, im) pairs"))
+    n = Ref{Cint}(0)
+    GC.@preserve raw begin
+        check(ccall((:tsdr_chain_push_host_i16, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cint}),
+                    c.handle, pointer(raw), length(raw) ÷ 2, n))
+        check(ccall((:tsdr_chain_sync, LIB), Cint, (Ptr{Cvoid},), c.handle))
+    end
+    return Int(n[])
+end
+
 function Base.push!(c::Chain, sigId::Vector{ComplexF32})
     n = Ref{Cint}(0)
     GC.@preserve sigId begin

@@ -178,6 +178,43 @@ def test_chain_bit_exact(synth, Fs, mode, frames, alpha):
     ch.close()
 
 
+def test_chain_int16_push_matches_widened_float_push(synth):
+    # `:short` recordings (src/DatBinaryFiles.jl:47-49): Int16 pairs widened without scaling; the device-side
+    # widening must give exactly what pushing the host-widened ComplexF32 buffer gives, and what the oracle gives
+    import torch
+    Fs, x_t, y_t, fv, frames = 20.0e6, 1056, 628, 60.0, 2
+    S = orc.frame_samples(Fs, fv)
+    n = S * frames + 5
+    cfg = tsdr.VideoMode(x_t, y_t, fv)
+    rng = np.random.default_rng(5)
+    a = tsdr.Chain(Fs, cfg, alpha=0.2, max_samples=n)
+    b = tsdr.Chain(Fs, cfg, alpha=0.2, max_samples=n)
+    d = tsdr.Chain(Fs, cfg, alpha=0.2, max_samples=n)
+    so = orc.SyncXY()
+    acc = np.zeros((600, 800), np.float32)
+    for k in range(3):  # three pushes: both landing buffers are reused
+        iq = synth.make_iq(n, Fs, x_t, y_t, fv, seed=40 + k, t0=k * n)
+        i16 = np.empty((n, 2), np.int16)
+        i16[:, 0] = np.clip(np.rint(iq.real * 9000.0), -32768, 32767)
+        i16[:, 1] = np.clip(np.rint(iq.imag * 9000.0), -32768, 32767)
+        i16[rng.integers(0, n, 8), 0] = [-32768, 32767, 0, -1, 1, -32768, 32767, 0]
+        wide = (i16[:, 0].astype(np.float32) + 1j * i16[:, 1].astype(np.float32)).astype(np.complex64)
+        acc, _, sy_ref, sx_ref = orc.chain_buffer(wide, Fs, x_t, y_t, fv, 0.2, so, acc)
+        assert a.push_i16(i16) == frames and b.push(wide) == frames
+        assert np.array_equal(a.image(), b.image()) and np.array_equal(a.image(), acc)
+        dev = torch.zeros(2 * n + 8, dtype=torch.int16, device="cuda")   # padded to whole 4-sample groups
+        dev[: 2 * n] = torch.from_numpy(i16.reshape(-1)).cuda()
+        assert d.push_device_i16(dev.data_ptr(), n) == frames
+        assert np.array_equal(d.image(), acc)
+        sy, sx = a.offsets()
+        assert np.array_equal(sy, sy_ref) and np.array_equal(sx, sx_ref)
+    with pytest.raises(tsdr.TempestError):
+        a.push_i16(np.zeros((n + 1, 2), np.int16))
+    with pytest.raises(tsdr.TempestError):
+        d.push_device_i16(dev.data_ptr() + 4, n - 1)   # not 16-byte aligned
+    a.close(); b.close(); d.close()
+
+
 def test_chain_overlap_modes_agree(synth):
     # three buffers through the two-stream pipeline and through the serial path: identical results
     Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)
