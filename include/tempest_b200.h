@@ -150,6 +150,13 @@ int tsdr_chain_push_device_i16(tsdr_chain* c, const int16_t* iq_dev, size_t n, i
 int tsdr_chain_push_host_deliver(tsdr_chain* c, const float* iq_host, size_t n, int* n_frames, float* image_out_host);
 int tsdr_chain_push_host_i16_deliver(tsdr_chain* c, const int16_t* iq_host, size_t n, int* n_frames, float* image_out_host);
 int tsdr_chain_wait_delivery(tsdr_chain* c, int age);
+/* Take the next buffer of a ring (below) and push it: the slot is borrowed, copied to the device straight from its
+ * page-locked memory and released when that copy has completed -- recv!(sigId, csdr) + the loop body (GUI.jl:163-176)
+ * without the intermediate sigId array.  TSDR_ERR_BOUNDS when no buffer arrives within timeout_ms (< 0: wait forever). */
+#define TSDR_SAMPLES_CF32 0   /* interleaved Float32 (re, im): ComplexF32 */
+#define TSDR_SAMPLES_CI16 1   /* interleaved Int16 (re, im) */
+typedef struct tsdr_ring tsdr_ring;
+int tsdr_chain_push_ring(tsdr_chain* c, tsdr_ring* r, int sample_format, int timeout_ms, int* n_frames);
 /* Run the frames of a buffer through render + sync search WITHOUT accumulating them: only
  * the SyncXY state (the stale beta_y of FrameSynchronisation.jl:66) advances.  A rank that
  * integrates frames k..k+F-1 of a long capture primes its chain with frame k-1 so that its
@@ -183,6 +190,34 @@ int tsdr_chain_launch_count(tsdr_chain* c, uint64_t* count);
 int tsdr_chain_set_profiling(tsdr_chain* c, int enable);
 int tsdr_chain_kernel_times(tsdr_chain* c, float ms[TSDR_CHAIN_STAGES], uint64_t pushes[1]);
 int tsdr_chain_destroy(tsdr_chain* c);
+
+/* ---- GetSpectrum.jl: the spectra used to find the leakage carrier, on the same FFT engine ----
+ * getSpectrum(fs, sig; N) (src/GetSpectrum.jl:21-30): y[N] = 10*log10.(abs2.(fftshift(fft(sig[1:N])))) of a ComplexF32
+ * signal (log_scale = 0: abs2 only); any N in [1, 2^23] (lengths that are not powers of two run as a chirp-z convolution).
+ * getWelch (:36-52): y[sizeFFT] = 10*log10.(fftshift(sum over the len/sizeFFT segments of abs2.(fft(segment)))).
+ * getWaterfall (:54-66): sMatrix (sizeFFT x nbSeg, column-major) = abs2.(fftshift(fft(segment))) per segment.
+ * sizeFFT: a power of two in [2, 8192].  The frequency / time axes are plain host arithmetic in the wrappers. */
+int tsdr_get_spectrum_f32(const float* sig_iq, size_t N, int log_scale, float* y);
+int tsdr_get_welch_f32(const float* sig_iq, size_t len, int size_fft, float* y);
+int tsdr_get_waterfall_f32(const float* sig_iq, size_t len, int size_fft, float* s_matrix);
+
+/* ---- buffer ring between the producer (radio / file) thread and the processing thread -----------------
+ * AtomicCircularBuffer{T}(nEch, depth) with circ_put! / circ_take! (src/AtomicAbstractSDRs.jl:67-190) in
+ * page-locked host memory: `depth` slots of slot_bytes each.  The producer never waits for the consumer and
+ * overwrites the slot at its write pointer; the consumer waits until a buffer is marked new and reads the slot
+ * at its read pointer.  One producer thread and one consumer thread.  pinned = 0: ordinary memory. */
+int tsdr_ring_create(tsdr_ring** out, size_t slot_bytes, int depth, int pinned);
+int tsdr_ring_destroy(tsdr_ring* r);
+int tsdr_ring_put(tsdr_ring* r, const void* data, size_t bytes);                  /* circ_put!  (:159-170) */
+int tsdr_ring_take(tsdr_ring* r, void* out, size_t bytes, int timeout_ms);        /* circ_take! (:176-189) */
+/* zero-copy forms: fill / read the slot in place */
+int tsdr_ring_acquire_write(tsdr_ring* r, void** slot);
+int tsdr_ring_commit(tsdr_ring* r);
+int tsdr_ring_acquire_read(tsdr_ring* r, const void** slot, int timeout_ms);
+int tsdr_ring_release_read(tsdr_ring* r);
+/* buffers marked new (t_new), totals, and buffers lost because the consumer lagged a whole ring */
+int tsdr_ring_stats(tsdr_ring* r, int* available, uint64_t* produced, uint64_t* consumed, uint64_t* overwritten);
+size_t tsdr_ring_slot_bytes(const tsdr_ring* r);
 
 /* Diagnostic: evaluates abs(::ComplexF32) on n pseudo-random operand pairs (seeded) twice,
  * once with the kernels' guard-free fast path and once with the IEEE intrinsics only

@@ -196,6 +196,44 @@ def calculate_autocorrelation(x, Fs, minDelay, maxDelay, scale="log"):  # src/Au
     return out[: n_out.value], lags
 
 
+def _freq_axis(n, fs):
+    return (np.arange(n, dtype=np.float64) / n - 0.5) * fs
+
+
+def _fftshift(v):  # circshift(v, div(n, 2))
+    return np.roll(v, v.shape[0] // 2, axis=0)
+
+
+def _abs2(z):  # abs2(::ComplexF32) = re*re + im*im in Float32
+    return (z.real * z.real + z.imag * z.imag).astype(np.float32)
+
+
+def getSpectrum(fs, sig, N=None):  # src/GetSpectrum.jl:21-30
+    sig = np.asarray(sig, np.complex64)
+    N = sig.size if N is None else N
+    y = np.float32(10) * np.log10(_abs2(_fftshift(fft(sig[:N])))).astype(np.float32)
+    return _freq_axis(N, fs), y
+
+
+def getWelch(fe, sig, sizeFFT=1024):  # src/GetSpectrum.jl:36-52
+    sig = np.asarray(sig, np.complex64)
+    S = np.zeros(sizeFFT, np.float32)
+    for n in range(sig.size // sizeFFT):
+        S += _abs2(fft(sig[n * sizeFFT:(n + 1) * sizeFFT]))     # S .+= abs2.(fft(ss)), segment order
+    with np.errstate(divide="ignore"):
+        y = np.float32(10) * np.log10(_fftshift(S)).astype(np.float32)
+    return _freq_axis(sizeFFT, fe), y
+
+
+def getWaterfall(fe, sig, sizeFFT=1024):  # src/GetSpectrum.jl:54-66
+    sig = np.asarray(sig, np.complex64)
+    nbSeg = sig.size // sizeFFT
+    sMatrix = np.zeros((sizeFFT, nbSeg), np.float64)
+    for iN in range(nbSeg):
+        sMatrix[:, iN] = _abs2(_fftshift(fft(sig[iN * sizeFFT:(iN + 1) * sizeFFT])))
+    return np.arange(nbSeg, dtype=np.float64) * (sizeFFT / fe), _freq_axis(sizeFFT, fe), sMatrix
+
+
 def zoom_autocorr(gamma, Fs, rate_min=20, rate_max=100):  # src/Autocorrelations.jl:42-53
     a, b = C.c_int64(0), C.c_int64(0)
     lib.orc_zoom_window(len(gamma), Fs, float(rate_min), float(rate_max), C.byref(a), C.byref(b))

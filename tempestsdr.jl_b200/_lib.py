@@ -71,6 +71,20 @@ SIGNATURES = {
     "tsdr_chain_set_profiling": (C.c_int, [_vp, C.c_int]),
     "tsdr_chain_kernel_times": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "tsdr_chain_destroy": (C.c_int, [_vp]),
+    "tsdr_get_spectrum_f32": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp]),
+    "tsdr_get_welch_f32": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp]),
+    "tsdr_get_waterfall_f32": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp]),
+    "tsdr_chain_push_ring": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _ip]),
+    "tsdr_ring_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_int]),
+    "tsdr_ring_destroy": (C.c_int, [_vp]),
+    "tsdr_ring_put": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "tsdr_ring_take": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int]),
+    "tsdr_ring_acquire_write": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "tsdr_ring_commit": (C.c_int, [_vp]),
+    "tsdr_ring_acquire_read": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.c_int]),
+    "tsdr_ring_release_read": (C.c_int, [_vp]),
+    "tsdr_ring_stats": (C.c_int, [_vp, _ip, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tsdr_ring_slot_bytes": (C.c_size_t, [_vp]),
     "tsdr_selftest_hypot": (C.c_int, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "tsdr_autocorr_plan_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_size_t, _vp]),
     "tsdr_autocorr_plan_exec": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),

@@ -17,10 +17,10 @@ from .video_configurations import (VideoMode, allVideoConfigurations, find_close
 
 __all__ = [
     "amDemod", "invert_amDemod", "fmDemod", "abs2", "sig_to_image", "downgradeImage", "naiveResampler", "init_resampler",
-    "calculate_autocorrelation", "zoom_autocorr", "findmax", "findmax_device", "sweep_refresh_hypotheses", "SyncXY", "vsync", "fullScale",
+    "calculate_autocorrelation", "zoom_autocorr", "getSpectrum", "getWelch", "getWaterfall", "findmax", "findmax_device", "sweep_refresh_hypotheses", "SyncXY", "vsync", "fullScale",
     "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
     "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
-    "Chain", "AutocorrPlan", "extract_configuration", "estimate_lines", "TempestError", "RENDERING_SIZE",
+    "Chain", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "TempestError", "RENDERING_SIZE",
     "device_count",
 ]
 
@@ -160,6 +160,44 @@ def zoom_autocorr(Gamma, Fs, rate_min=20, rate_max=100):
     pos_rate_max = min(_round(1 / rate_min * Fs), N)
     xAx = np.arange(pos_rate_min, pos_rate_max + 1, dtype=np.float64) / Fs
     return 1.0 / xAx, np.asarray(Gamma)[pos_rate_min - 1: pos_rate_max]
+
+
+def _freq_axis(n, fs):  # collect(((0:N-1)./N .- 0.5)*fs)
+    return (np.arange(n, dtype=np.float64) / n - 0.5) * fs
+
+
+def getSpectrum(fs, sig=None, N=None):
+    """(freqAx, y) -- src/GetSpectrum.jl:21-30; getSpectrum(sig) = getSpectrum(1, sig) (:31)"""
+    if sig is None:
+        fs, sig = 1, fs
+    z, n = _iq(sig)
+    if N is None:
+        N = n
+    if N > n:
+        raise IndexError("BoundsError: sig[1:%d] of a %d-sample signal" % (N, n))
+    y = np.empty(N, np.float32)
+    check(_lib.load().tsdr_get_spectrum_f32(_ptr(z), int(N), 1, _ptr(y)))
+    return _freq_axis(N, fs), y
+
+
+def getWelch(fe, sig, sizeFFT=1024):
+    """(freqAx, y) -- src/GetSpectrum.jl:36-52"""
+    z, n = _iq(sig)
+    y = np.empty(sizeFFT, np.float32)
+    check(_lib.load().tsdr_get_welch_f32(_ptr(z), n, int(sizeFFT), _ptr(y)))
+    return _freq_axis(sizeFFT, fe), y
+
+
+def getWaterfall(fe, sig=None, sizeFFT=1024):
+    """(tAx, fAx, sMatrix[sizeFFT, nbSeg]) -- src/GetSpectrum.jl:54-67; the matrix is Float64 like the reference's"""
+    if sig is None:
+        fe, sig = 1, fe
+    z, n = _iq(sig)
+    nbSeg = n // sizeFFT
+    s = np.empty((nbSeg, sizeFFT), np.float32)   # column-major sizeFFT x nbSeg
+    check(_lib.load().tsdr_get_waterfall_f32(_ptr(z), n, int(sizeFFT), _ptr(s)))
+    tAx = np.arange(nbSeg, dtype=np.float64) * (sizeFFT / fe)
+    return tAx, _freq_axis(sizeFFT, fe), s.T.astype(np.float64)
 
 
 def findmax(v):
@@ -332,6 +370,13 @@ class Chain:
         check(_lib.load().tsdr_chain_push_host_i16_deliver(self._h, C.c_void_p(iq16_ptr), int(n), C.byref(nf), C.c_void_p(image_out_ptr)))
         return nf.value
 
+    def push_ring(self, ring, timeout_ms=-1):
+        """recv! + loop body: take the ring's next buffer and push it straight from its page-locked slot"""
+        nf = C.c_int(0)
+        fmt = 0 if ring.dtype == np.complex64 else 1
+        check(_lib.load().tsdr_chain_push_ring(self._h, ring._h, fmt, int(timeout_ms), C.byref(nf)))
+        return nf.value
+
     def wait_delivery(self, age=0):
         check(_lib.load().tsdr_chain_wait_delivery(self._h, int(age)))
 
@@ -410,6 +455,65 @@ class Chain:
             self._h = None
 
     __del__ = close
+
+
+class AtomicCircularBuffer:
+    """AtomicCircularBuffer{T}(nEch, depth) (src/AtomicAbstractSDRs.jl:67-79) in page-locked host memory.
+
+    dtype: numpy complex64 (one recv! buffer of nEch ComplexF32 samples per slot) or int16 (nEch (re, im) Int16
+    pairs per slot).  pinned=False allocates ordinary memory (hosts without a GPU)."""
+
+    def __init__(self, nEch, depth, dtype=np.complex64, pinned=True):
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.complex64), np.dtype(np.int16)):
+            raise TypeError("ring slots hold complex64 or int16 (re, im) samples")
+        self.nEch, self.depth = int(nEch), int(depth)
+        self.sample_bytes = 8 if self.dtype == np.complex64 else 4
+        h = C.c_void_p()
+        check(_lib.load().tsdr_ring_create(C.byref(h), self.nEch * self.sample_bytes, self.depth, 1 if pinned else 0))
+        self._h = h
+
+    def _flat(self, data):
+        z = np.ascontiguousarray(data, dtype=self.dtype).reshape(-1)
+        if z.nbytes != self.nEch * self.sample_bytes:  # the reference asserts equal lengths (:113)
+            raise ValueError("buffer of %d bytes does not match the ring's slot of %d samples" % (z.nbytes, self.nEch))
+        return z
+
+    def put(self, data):
+        """circ_put! (:159-170): never waits for the consumer"""
+        z = self._flat(data)
+        check(_lib.load().tsdr_ring_put(self._h, _ptr(z), z.nbytes))
+
+    def take(self, out=None, timeout_ms=-1):
+        """circ_take! (:176-189): waits for a new buffer, copies it out"""
+        if out is None:
+            out = np.empty(self.nEch if self.dtype == np.complex64 else 2 * self.nEch, self.dtype)
+        if not (isinstance(out, np.ndarray) and out.flags.c_contiguous and out.dtype == self.dtype
+                and out.nbytes == self.nEch * self.sample_bytes):
+            raise ValueError("out must be a contiguous %s array of one slot" % self.dtype)
+        check(_lib.load().tsdr_ring_take(self._h, _ptr(out), out.nbytes, int(timeout_ms)))
+        return out
+
+    def stats(self):
+        n = C.c_int(0)
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(_lib.load().tsdr_ring_stats(self._h, C.byref(n), C.byref(a), C.byref(b), C.byref(c)))
+        return {"available": n.value, "produced": a.value, "consumed": b.value, "overwritten": c.value}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().tsdr_ring_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def circ_put(circ_buff, data):
+    circ_buff.put(data)
+
+
+def circ_take(buffer, circ_buff, timeout_ms=-1):
+    return circ_buff.take(buffer, timeout_ms)
 
 
 class AutocorrPlan:

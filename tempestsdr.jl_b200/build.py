@@ -22,6 +22,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "--threads", "2", "-Xcompiler", "-fP
 UNITS = [
     ("tsdr_core.cu", ["-fmad=false"]),
     ("tsdr_fft.cu", ["-fmad=true"]),
+    ("tsdr_ring.cu", []),
 ]
 
 

@@ -1032,6 +1032,25 @@ int tsdr_chain_push_host_i16_deliver(tsdr_chain* c, const int16_t* iq_host, size
     return chain_push_deliver(c, iq_host, n, n_frames, image_out_host, true);
 }
 
+int tsdr_chain_push_ring(tsdr_chain* c, tsdr_ring* r, int sample_format, int timeout_ms, int* n_frames) {
+    TSDR_REQUIRE(c && r, "NULL argument");
+    TSDR_REQUIRE(sample_format == TSDR_SAMPLES_CF32 || sample_format == TSDR_SAMPLES_CI16, "unknown sample format %d", sample_format);
+    const size_t bps = sample_format == TSDR_SAMPLES_CI16 ? 4 : 8;
+    const size_t n = tsdr_ring_slot_bytes(r) / bps;
+    const void* slot = nullptr;
+    int rc = tsdr_ring_acquire_read(r, &slot, timeout_ms);
+    if (rc) return rc;
+    rc = sample_format == TSDR_SAMPLES_CI16 ? tsdr_chain_push_host_i16(c, (const int16_t*)slot, n, n_frames)
+                                            : tsdr_chain_push_host(c, (const float*)slot, n, n_frames);
+    // the producer may rewrite the slot as soon as it is released: wait for the H2D copy (not for the kernels)
+    cudaError_t e = cudaSuccess;
+    if (rc == TSDR_OK && n / (size_t)c->S) e = cudaEventSynchronize(c->ev_copied[c->stage_parity ^ 1]);
+    const int rc2 = tsdr_ring_release_read(r);
+    if (rc) return rc;
+    TSDR_CUDA(e);
+    return rc2;
+}
+
 int tsdr_chain_wait_delivery(tsdr_chain* c, int age) {
     TSDR_REQUIRE(c && (age == 0 || age == 1), "age must be 0 (latest delivery) or 1 (the one before)");
     TSDR_CUDA(cudaSetDevice(c->device));

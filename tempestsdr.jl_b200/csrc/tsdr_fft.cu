@@ -191,6 +191,12 @@ struct FftParams {
     int64_t n_in;          // input samples (M = n_in * up)
     const double2* Hd;     // [M] filter in ComplexF64, natural frequency order
     float gain;            // 2 * upCoeff
+    // mode 3: power spectrum of a complex M-point signal (getSpectrum, src/GetSpectrum.jl:21-30): forward transform,
+    //         abs2, 10 log10, fftshift -- no inverse.
+    // mode 2: the same for a length n_in that is not a power of two, as a chirp-z (Bluestein) convolution on the
+    //         M >= 2 n_in - 1 point engine: x[j] conj(b[j]) -> FFT -> * FFT(b) (Hd) -> IFFT; |X[k]|^2 = |y[k]|^2
+    //         because the final chirp factor has unit modulus.  b[j] = exp(i pi j^2 / n_in).
+    const float2* chirp;   // [n_in] b[j]
 };
 
 __device__ __forceinline__ float2 twiddle_n(const FftParams& p, int64_t t) {  // W_N^t, 0 <= t < N
@@ -219,6 +225,11 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_cols(FftParams p) {
             const int64_t q = j / p.up;
             v.x = (q * p.up == j && q < p.n_in) ? __ldg(p.x + q) : 0.f;
             v.y = 0.f;
+        } else if (p.mode == 3) {
+            v = __ldg(reinterpret_cast<const float2*>(p.x) + j);
+        } else if (p.mode == 2) {
+            v = make_float2(0.f, 0.f);
+            if (j < p.n_in) v = cmul(__ldg(reinterpret_cast<const float2*>(p.x) + j), cconj(__ldg(p.chirp + j)));
         } else if (2 * j + 1 < p.n_valid) v = __ldg(reinterpret_cast<const float2*>(p.x) + j);
         else { v.x = (2 * j < p.n_valid) ? __ldg(p.x + 2 * j) : 0.f; v.y = 0.f; }
         sm[lay(col, j1)] = v;
@@ -256,7 +267,19 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_mid(FftParams p) {
 
     // real-input unpack, |X|^2, Hermitian repack (pairs k <-> M-k), scaled by 1/M
     const float sc = 0.5f * p.inv_scale;
-    if (p.mode == 1) {
+    if (p.mode == 3) {   // 10*log10.(abs2.(fftshift(fft(ss))))  (GetSpectrum.jl:28)
+        for (int e = tid; e < nrows * p.B; e += kFftThreads) {
+            const int r = e / p.B, pos = e - r * p.B;
+            const int64_t k = (int64_t)(r == 0 ? k1a : k1b) + (int64_t)p.A * __ldg(p.revB + pos);
+            const float2 z = sm[lay(r, pos)];
+            const float P = z.x * z.x + z.y * z.y;
+            int64_t i = k + p.M / 2;
+            if (i >= p.M) i -= p.M;
+            p.out[i] = p.log_scale ? 10.0f * log10f(P) : P;
+        }
+        return;
+    }
+    if (p.mode == 1 || p.mode == 2) {
         // inFFT[n] = inFFT[n] * H[n]: ComplexF32 * ComplexF64 in Float64, rounded to ComplexF32 (Resampler.jl:51-53);
         // the 1/M of the scaled inverse plan is applied here
         for (int e = tid; e < nrows * p.B; e += kFftThreads) {
@@ -353,6 +376,16 @@ __global__ void __launch_bounds__(kFftThreads) k_ifft_cols(FftParams p) {
         const int j1 = e / p.C, col = e - j1 * p.C;
         const int64_t j = (int64_t)j1 * p.B + j2_0 + col;
         if (p.mode == 1) { p.out[j] = p.gain * sm[lay(col, j1)].x; continue; }  // out[n] = 2*upCoeff*real(outFFT[n])  (Resampler.jl:57-59)
+        if (p.mode == 2) {
+            if (j < p.n_in) {
+                const float2 z = sm[lay(col, j1)];
+                const float P = z.x * z.x + z.y * z.y;
+                int64_t i = j + p.n_in / 2;
+                if (i >= p.n_in) i -= p.n_in;
+                p.out[i] = p.log_scale ? 10.0f * log10f(P) : P;
+            }
+            continue;
+        }
         const int64_t m0 = 2 * j;
         if (m0 > p.m_hi || m0 + 1 < p.m_lo) continue;
         const float2 v = sm[lay(col, j1)];
@@ -377,6 +410,86 @@ __global__ void __launch_bounds__(256) k_fold_lags(const float* __restrict__ lin
     float v = r * r;
     if (log_scale) v = 10.0f * log10f(v);
     out[i] = v;
+}
+
+
+// ----------------------------------------------------------- k_spec_batch --
+// getWelch / getWaterfall (src/GetSpectrum.jl:36-66): the signal is cut into segments of `len`
+// samples (a power of two), each gets a forward FFT in shared memory (`rows` segments per pass).
+//  mode 0 (waterfall): out[seg][i] = abs2(fftshift(fft(seg)))[i]
+//  mode 1 (Welch):     every thread keeps the running sum over the CTA's segments of the bins it
+//                      owns (segments added in order), partial[cta][i] -> k_welch_final
+struct SpecParams {
+    const float2* x;
+    int len;
+    Radices rad;
+    const float2* tw;      // W_len^k
+    const int* pos;        // frequency -> position after the in-place DIF
+    int64_t nseg;
+    int rows;              // segments transformed per pass
+    int seg_per_cta;
+    int mode;
+    float* out;            // waterfall [nseg][len]
+    float* partial;        // Welch [gridDim.x][len]
+};
+constexpr int kSpecThreads = 256;
+constexpr int kSpecMaxBins = 32;  // len <= 8192
+
+__global__ void __launch_bounds__(kSpecThreads) k_spec_batch(SpecParams p) {
+    extern __shared__ float2 sm[];
+    const int tid = threadIdx.x;
+    const int rs = row_padded(p.len);
+    const RowLayout lay{rs};
+    const int64_t s_begin = (int64_t)blockIdx.x * p.seg_per_cta;
+    const int64_t s_end = min(p.nseg, s_begin + p.seg_per_cta);
+    const int half = p.len / 2;
+    float acc[kSpecMaxBins];
+#pragma unroll
+    for (int q = 0; q < kSpecMaxBins; ++q) acc[q] = 0.f;
+    for (int64_t g = s_begin; g < s_end; g += p.rows) {
+        const int nb = (int)min((int64_t)p.rows, s_end - g);
+        for (int e = tid; e < nb * p.len; e += kSpecThreads) {
+            const int b = e / p.len, i = e - b * p.len;
+            sm[lay(b, i)] = __ldg(p.x + (g + b) * p.len + i);
+        }
+        __syncthreads();
+        fft_inplace<+1, false>(sm, lay, nb, p.len, p.rad, p.tw, tid, kSpecThreads);
+        if (p.mode == 0) {
+            for (int e = tid; e < nb * p.len; e += kSpecThreads) {
+                const int b = e / p.len, i = e - b * p.len;
+                const int k = i >= half ? i - half : i + half;       // fftshift, even length
+                const float2 z = sm[lay(b, __ldg(p.pos + k))];
+                p.out[(g + b) * p.len + i] = z.x * z.x + z.y * z.y;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < kSpecMaxBins; ++q) {
+                const int i = q * kSpecThreads + tid;
+                if (i < p.len) {
+                    const int k = i >= half ? i - half : i + half;
+                    const int ps = __ldg(p.pos + k);
+                    for (int b = 0; b < nb; ++b) { const float2 z = sm[lay(b, ps)]; acc[q] += z.x * z.x + z.y * z.y; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (p.mode == 1) {
+#pragma unroll
+        for (int q = 0; q < kSpecMaxBins; ++q) {
+            const int i = q * kSpecThreads + tid;
+            if (i < p.len) p.partial[(int64_t)blockIdx.x * p.len + i] = acc[q];
+        }
+    }
+}
+
+// S = sum of the CTA partials in segment order; y = 10*log10.(fftshift(S))  (GetSpectrum.jl:49)
+__global__ void __launch_bounds__(256) k_welch_final(const float* __restrict__ partial, int nparts, int len, float* __restrict__ y) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= len) return;
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += partial[(int64_t)c * len + i];
+    y[i] = 10.0f * log10f(s);
 }
 
 }  // namespace tsdr
@@ -751,6 +864,125 @@ int tsdr_autocorr_f32(const float* x, size_t len, double Fs, double min_delay, d
     cudaFree(d_x); cudaFree(d_out);
     tsdr_autocorr_plan_destroy(plan);
     return rc;
+}
+
+
+// ---------------------------------------------------------------- GetSpectrum.jl --
+// getSpectrum(fs, sig; N) (src/GetSpectrum.jl:21-30): y = 10*log10.(abs2.(fftshift(fft(sig[1:N])))) for a
+// ComplexF32 signal.  Powers of two >= 32 go straight through the complex engine; every other
+// length is evaluated as a chirp-z convolution on the next power of two >= 2N-1.
+int tsdr_get_spectrum_f32(const float* sig_iq, size_t N, int log_scale, float* y) {
+    TSDR_REQUIRE((sig_iq && y) || N == 0, "NULL argument");
+    if (N == 0) return TSDR_OK;
+    TSDR_REQUIRE(N <= ((size_t)1 << 23), "getSpectrum: at most 2^23 samples");
+    int rc = ensure_device(); if (rc) return rc;
+    const bool direct = is_pow2(N) && N >= 32;
+    size_t M = N;
+    if (!direct) { M = 32; while (M < 2 * N - 1) M <<= 1; }
+    tsdr_autocorr_plan* plan = nullptr;
+    if ((rc = tsdr_autocorr_plan_create(&plan, current_device(), 2 * M, nullptr))) return rc;
+    void *d_x = nullptr, *d_y = nullptr, *d_chirp = nullptr, *d_H = nullptr;
+    cudaError_t e = cudaMalloc(&d_x, N * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&d_y, N * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, sig_iq, N * sizeof(float2), cudaMemcpyHostToDevice, plan->stream);
+    FftParams fp = plan->fp;
+    fp.x = (const float*)d_x; fp.n_in = (int64_t)N; fp.out = (float*)d_y; fp.log_scale = log_scale; fp.n_valid = 0;
+    if (direct) fp.mode = 3;
+    else {
+        // b[j] = exp(i pi j^2 / N), phase from j^2 mod 2N so that it keeps full precision for large j
+        std::vector<float2> chirp(N);
+        std::vector<double> re(M, 0.0), im(M, 0.0);
+        const double PI = 3.14159265358979323846264338327950288;
+        for (size_t j = 0; j < N; ++j) {
+            const unsigned long long q = (unsigned long long)(((unsigned __int128)j * j) % (2 * (unsigned __int128)N));
+            const double ph = PI * (double)q / (double)N;
+            const double c = cos(ph), sn = sin(ph);
+            chirp[j] = make_float2((float)c, (float)sn);
+            re[j] = c; im[j] = sn;
+            if (j) { re[M - j] = c; im[M - j] = sn; }
+        }
+        host_fft(re, im, false);
+        std::vector<double2> H(M);
+        for (size_t k = 0; k < M; ++k) H[k] = make_double2(re[k], im[k]);
+        if (e == cudaSuccess) e = cudaMalloc(&d_chirp, N * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&d_H, M * sizeof(double2));
+        if (e == cudaSuccess) e = cudaMemcpy(d_chirp, chirp.data(), N * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_H, H.data(), M * sizeof(double2), cudaMemcpyHostToDevice);
+        fp.mode = 2; fp.chirp = (const float2*)d_chirp; fp.Hd = (const double2*)d_H;
+    }
+    if (e == cudaSuccess) {
+        cudaStream_t st = plan->stream;
+        k_fft_cols<<<fp.B / fp.C, kFftThreads, plan->smem_cols, st>>>(fp);
+        k_fft_mid<<<fp.A / 2 + 1, kFftThreads, plan->smem_mid, st>>>(fp);
+        if (!direct) k_ifft_cols<<<fp.B / fp.C, kFftThreads, plan->smem_cols, st>>>(fp);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(y, d_y, N * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) rc = cuda_fail(e, "tsdr_get_spectrum_f32", __FILE__, __LINE__);
+    cudaFree(d_x); cudaFree(d_y); cudaFree(d_chirp); cudaFree(d_H);
+    tsdr_autocorr_plan_destroy(plan);
+    return rc;
+}
+
+namespace tsdr {
+// getWelch (mode 1) / getWaterfall (mode 0): nbSeg = len / sizeFFT segments, the tail is dropped (:39, :55)
+static int spec_segments(const float* sig_iq, size_t len, int size_fft, int mode, float* out) {
+    TSDR_REQUIRE(size_fft >= 2 && size_fft <= 8192 && is_pow2((size_t)size_fft),
+                 "sizeFFT must be a power of two in [2, 8192] (got %d)", size_fft);
+    const int64_t nseg = (int64_t)(len / (size_t)size_fft);
+    TSDR_REQUIRE((sig_iq && out) || nseg == 0, "NULL argument");
+    int rc = ensure_device(); if (rc) return rc;
+    SpecParams sp;
+    sp.len = size_fft; sp.rad = make_radices(size_fft); sp.nseg = nseg; sp.mode = mode;
+    sp.rows = std::max(1, 8192 / size_fft);
+    std::vector<float2> tw(size_fft);
+    std::vector<int> pos(size_fft);
+    const double PI2 = 6.283185307179586476925286766559;
+    for (int k = 0; k < size_fft; ++k) { tw[k].x = (float)cos(PI2 * k / size_fft); tw[k].y = (float)-sin(PI2 * k / size_fft); }
+    for (int i = 0; i < size_fft; ++i) pos[dif_frequency(i, size_fft, sp.rad)] = i;
+    // enough CTAs to fill the GPU, whole passes of `rows` segments each
+    int64_t ctas = std::min<int64_t>((nseg + sp.rows - 1) / sp.rows, 148 * 4);
+    if (ctas < 1) ctas = 1;
+    sp.seg_per_cta = (int)(((nseg + ctas - 1) / ctas + sp.rows - 1) / sp.rows * sp.rows);
+    if (sp.seg_per_cta < sp.rows) sp.seg_per_cta = sp.rows;
+    ctas = nseg ? (nseg + sp.seg_per_cta - 1) / sp.seg_per_cta : 1;
+    const size_t smem = (size_t)sp.rows * row_padded(size_fft) * sizeof(float2);
+    const size_t n_used = (size_t)nseg * size_fft;
+    const size_t out_floats = mode == 0 ? n_used : (size_t)size_fft;
+    void *d_x = nullptr, *d_out = nullptr, *d_part = nullptr, *d_tab = nullptr;
+    cudaError_t e = cudaMalloc(&d_x, std::max<size_t>(n_used, 1) * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, std::max<size_t>(out_floats, 1) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_part, (size_t)ctas * size_fft * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tab, size_fft * (sizeof(float2) + sizeof(int)));
+    if (e == cudaSuccess && n_used) e = cudaMemcpy(d_x, sig_iq, n_used * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_tab, tw.data(), size_fft * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((char*)d_tab + size_fft * sizeof(float2), pos.data(), size_fft * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spec_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        sp.x = (const float2*)d_x; sp.tw = (const float2*)d_tab; sp.pos = (const int*)((char*)d_tab + size_fft * sizeof(float2));
+        sp.out = (float*)d_out; sp.partial = (float*)d_part;
+        if (nseg) k_spec_batch<<<(unsigned)ctas, kSpecThreads, smem>>>(sp);
+        else e = cudaMemset(d_part, 0, (size_t)size_fft * sizeof(float));   // no segment: S stays zeros -> -Inf dB, as the reference
+        if (mode == 1) k_welch_final<<<(size_fft + 255) / 256, 256>>>((const float*)d_part, (int)ctas, size_fft, (float*)d_out);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess && out_floats) e = cudaMemcpy(out, d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    if (e != cudaSuccess) rc = cuda_fail(e, "spec_segments", __FILE__, __LINE__);
+    cudaFree(d_x); cudaFree(d_out); cudaFree(d_part); cudaFree(d_tab);
+    return rc;
+}
+}  // namespace tsdr
+
+// getWelch(fe, sig; sizeFFT) (src/GetSpectrum.jl:36-52): y[sizeFFT] = 10*log10.(fftshift(sum_n abs2.(fft(seg_n))))
+int tsdr_get_welch_f32(const float* sig_iq, size_t len, int size_fft, float* y) {
+    return spec_segments(sig_iq, len, size_fft, 1, y);
+}
+
+// getWaterfall(fe, sig; sizeFFT) (src/GetSpectrum.jl:54-66): sMatrix[:, n] = abs2.(fftshift(fft(seg_n))), column-major
+// sizeFFT x nbSeg (Float32 here; the reference widens the same Float32 values into a Float64 matrix)
+int tsdr_get_waterfall_f32(const float* sig_iq, size_t len, int size_fft, float* s_matrix) {
+    return spec_segments(sig_iq, len, size_fft, 0, s_matrix);
 }
 
 }  // extern "C"

@@ -12,7 +12,8 @@
 module TempestSDRB200
 
 export amDemod, invert_amDemod, sig_to_image, downgradeImage, naiveResampler, init_resampler,
-       calculate_autocorrelation, zoom_autocorr, SyncXY, vsync, Chain, push!, image, offsets
+       calculate_autocorrelation, zoom_autocorr, SyncXY, vsync, Chain, push!, image, offsets,
+       AtomicCircularBuffer, circ_put!, circ_take!, push_ring!, getSpectrum, getWelch, getWaterfall
 
 const LIB = get(ENV, "TEMPEST_B200_LIB", joinpath(@__DIR__, "..", "libtempest_b200.so"))
 const RENDERING_SIZE = (600, 800)                      # src/GUI.jl:10
@@ -199,6 +200,73 @@ end
 configure!(c::Chain, Fs, x_t, y_t, fv) = check(ccall((:tsdr_chain_configure, LIB), Cint,
                                                      (Ptr{Cvoid}, Cdouble, Cint, Cint, Cdouble), c.handle, Fs, x_t, y_t, fv))
 set_alpha!(c::Chain, α) = check(ccall((:tsdr_chain_set_alpha, LIB), Cint, (Ptr{Cvoid}, Cfloat), c.handle, α))
+
+# ---- GetSpectrum.jl (src/GetSpectrum.jl:21-66) -------------------------------------------------------------
+function getSpectrum(fs, sig::Vector{ComplexF32}; N = nothing)
+    isnothing(N) && (N = length(sig))
+    N <= length(sig) || throw(BoundsError(sig, 1:N))
+    freqAx = collect(((0:N-1) ./ N .- 0.5) * fs)
+    y = Vector{Float32}(undef, N)
+    GC.@preserve sig y check(ccall((:tsdr_get_spectrum_f32, LIB), Cint, (Ptr{Cvoid}, Csize_t, Cint, Ptr{Cvoid}),
+                                   pointer(sig), N, 1, pointer(y)))
+    return (freqAx, y)
+end
+getSpectrum(sig) = getSpectrum(1, sig)
+
+function getWelch(fe, sig::Vector{ComplexF32}; sizeFFT = 1024)
+    y = Vector{Float32}(undef, sizeFFT)
+    GC.@preserve sig y check(ccall((:tsdr_get_welch_f32, LIB), Cint, (Ptr{Cvoid}, Csize_t, Cint, Ptr{Cvoid}),
+                                   pointer(sig), length(sig), sizeFFT, pointer(y)))
+    return (collect(((0:sizeFFT-1) ./ sizeFFT .- 0.5) * fe), y)
+end
+
+function getWaterfall(fe, sig::Vector{ComplexF32}; sizeFFT = 1024)
+    nbSeg = length(sig) ÷ sizeFFT
+    s = Matrix{Float32}(undef, sizeFFT, nbSeg)
+    GC.@preserve sig s check(ccall((:tsdr_get_waterfall_f32, LIB), Cint, (Ptr{Cvoid}, Csize_t, Cint, Ptr{Cvoid}),
+                                   pointer(sig), length(sig), sizeFFT, pointer(s)))
+    fAx = collect(((0:1:sizeFFT-1) ./ sizeFFT .- 0.5) .* fe)
+    tAx = (0:nbSeg-1) * (sizeFFT / fe)
+    return tAx, fAx, Float64.(s)
+end
+getWaterfall(sig; sizeFFT = 1024) = getWaterfall(1, sig; sizeFFT = sizeFFT)
+
+# ---- AtomicCircularBuffer (src/AtomicAbstractSDRs.jl:67-190) in page-locked memory ------------------------
+# Same constructor and circ_put! / circ_take! as the reference, so start_atomic_sdr (:284-306) and recv!
+# (:312-314) keep working unchanged; push_ring!(chain, ring) replaces recv! + the loop body (GUI.jl:163-176)
+# and copies to the GPU straight from the ring's slot.
+mutable struct AtomicCircularBuffer{T}
+    handle::Ptr{Cvoid}
+    nEch::Int
+    depth::Int
+    function AtomicCircularBuffer{T}(nEch::Int, depth::Int) where T
+        T === ComplexF32 || T === Complex{Int16} || throw(ArgumentError("ring slots hold ComplexF32 or Complex{Int16}"))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:tsdr_ring_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Csize_t, Cint, Cint), h, nEch * sizeof(T), depth, 1))
+        r = new{T}(h[], nEch, depth)
+        finalizer(x -> ccall((:tsdr_ring_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), r)
+        return r
+    end
+end
+
+function circ_put!(circ_buff::AtomicCircularBuffer{T}, data::Vector{T}) where T          # :159-170
+    GC.@preserve data check(ccall((:tsdr_ring_put, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t),
+                                  circ_buff.handle, pointer(data), sizeof(data)))
+end
+
+function circ_take!(buffer::Vector{T}, circ_buff::AtomicCircularBuffer{T}) where T       # :176-189
+    # @threadcall: the wait for new data must not block the Julia scheduler the producer task runs on
+    GC.@preserve buffer check(@threadcall((:tsdr_ring_take, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Cint),
+                                          circ_buff.handle, pointer(buffer), sizeof(buffer), -1))
+end
+
+function push_ring!(c::Chain, ring::AtomicCircularBuffer{T}; timeout_ms = -1) where T
+    n = Ref{Cint}(0)
+    fmt = T === ComplexF32 ? 0 : 1
+    check(@threadcall((:tsdr_chain_push_ring, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Cint}),
+                      c.handle, ring.handle, fmt, timeout_ms, n))
+    return Int(n[])
+end
 
 # Rebind the reference module's DSP functions to the GPU versions (same names, same signatures).
 function use!(ref::Module)

@@ -215,6 +215,77 @@ def test_chain_int16_push_matches_widened_float_push(synth):
     a.close(); b.close(); d.close()
 
 
+def _carrier_signal(n, seed):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    return x + (4 * np.exp(2j * np.pi * 0.2137 * np.arange(n))).astype(np.complex64)
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 1000, 4096, 80000, 1 << 17])
+def test_getSpectrum_matches_oracle(N):
+    # src/GetSpectrum.jl:21-30.  Float32 FFTs of different factorisations (and the chirp-z route for lengths that
+    # are not powers of two) agree to ~1e-6 of the largest bin: compare in dB on the bins within 60 dB of the peak
+    x = _carrier_signal(max(N, 8) + 5, N)
+    f, y = tsdr.getSpectrum(2.0e6, x, N=N)
+    f_ref, y_ref = orc.getSpectrum(2.0e6, x, N=N)
+    assert y.dtype == np.float32 and np.array_equal(f, f_ref)
+    strong = y_ref > y_ref.max() - 60
+    assert np.abs(y[strong] - y_ref[strong]).max() < 2e-2
+    assert int(np.argmax(y)) == int(np.argmax(y_ref))
+    with pytest.raises(IndexError):
+        tsdr.getSpectrum(1.0, x, N=x.size + 1)
+
+
+@pytest.mark.parametrize("sizeFFT,n", [(1024, 80000), (64, 1000), (8192, 8192 * 3 + 17), (2, 11), (256, 100)])
+def test_getWelch_and_getWaterfall_match_oracle(sizeFFT, n):
+    # src/GetSpectrum.jl:36-66
+    x = _carrier_signal(n, sizeFFT)
+    f, y = tsdr.getWelch(2.0e6, x, sizeFFT=sizeFFT)
+    f_ref, y_ref = orc.getWelch(2.0e6, x, sizeFFT=sizeFFT)
+    assert np.array_equal(f, f_ref) and y.shape == y_ref.shape
+    if n >= sizeFFT:
+        strong = y_ref > y_ref.max() - 60
+        assert np.abs(y[strong] - y_ref[strong]).max() < 1e-2
+    else:
+        assert np.all(np.isneginf(y)) and np.all(np.isneginf(y_ref))     # no segment: 10*log10(0)
+    t, f, s = tsdr.getWaterfall(2.0e6, x, sizeFFT=sizeFFT)
+    t_ref, f_ref, s_ref = orc.getWaterfall(2.0e6, x, sizeFFT=sizeFFT)
+    assert s.dtype == np.float64 and s.shape == s_ref.shape and np.array_equal(t, t_ref) and np.array_equal(f, f_ref)
+    if s.size:
+        assert np.abs(s - s_ref).max() <= 5e-6 * s_ref.max()
+    with pytest.raises(tsdr.TempestError):
+        tsdr.getWelch(1.0, x, sizeFFT=1000)                               # not a power of two
+
+
+def test_chain_push_ring_pinned_slots(synth):
+    # producer thread -> page-locked ring -> push_ring: same images as pushing the buffers directly, both formats
+    import threading
+    Fs, x_t, y_t, fv, frames = 20.0e6, 1056, 628, 60.0, 2
+    S = orc.frame_samples(Fs, fv)
+    n = S * frames
+    cfg = tsdr.VideoMode(x_t, y_t, fv)
+    bufs = [synth.make_iq(n, Fs, x_t, y_t, fv, seed=70 + k, t0=k * n) for k in range(5)]
+    for dtype in (np.complex64, np.int16):
+        if dtype == np.int16:
+            data = [np.stack([np.rint(b.real * 8000), np.rint(b.imag * 8000)], axis=1).astype(np.int16) for b in bufs]
+        else:
+            data = bufs
+        ring = tsdr.AtomicCircularBuffer(n, 8, dtype=dtype, pinned=True)   # deep enough: nothing is overwritten
+        a = tsdr.Chain(Fs, cfg, alpha=0.3, max_samples=n)
+        b = tsdr.Chain(Fs, cfg, alpha=0.3, max_samples=n)
+        t = threading.Thread(target=lambda: [ring.put(d) for d in data])
+        t.start()
+        for d in data:
+            assert a.push_ring(ring, timeout_ms=5000) == frames
+            assert (b.push_i16(d) if dtype == np.int16 else b.push(d)) == frames
+            assert np.array_equal(a.image(), b.image())
+        t.join()
+        with pytest.raises(tsdr.TempestError):
+            a.push_ring(ring, timeout_ms=10)                                # drained
+        assert ring.stats()["overwritten"] == 0
+        a.close(); b.close(); ring.close()
+
+
 def test_chain_overlap_modes_agree(synth):
     # three buffers through the two-stream pipeline and through the serial path: identical results
     Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)

@@ -182,3 +182,25 @@ def test_oracle_chain_reproduces_golden(synth):
     assert np.array_equal(sy, GOLD["chain_sy"]) and np.array_equal(sx, GOLD["chain_sx"])
     assert np.array_equal(_sha(acc), GOLD["chain_image_sha256"])
     assert np.array_equal(_sha(so.beta_x()), GOLD["chain_beta_x_last_sha256"])
+
+
+def test_get_spectrum_family_against_numpy():
+    # src/GetSpectrum.jl:21-66 restated on the oracle's own FFT, checked here against numpy's double FFT
+    rng = np.random.default_rng(21)
+    n = 5000
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    x += (3 * np.exp(2j * np.pi * 0.12 * np.arange(n))).astype(np.complex64)
+    f, y = orc.getSpectrum(2.0e6, x, N=3000)                       # not a power of two
+    X = np.fft.fftshift(np.fft.fft(x[:3000].astype(np.complex128)))
+    assert y.dtype == np.float32 and y.shape == (3000,)
+    assert np.allclose(f, (np.arange(3000) / 3000 - 0.5) * 2.0e6)
+    assert np.abs(y - 10 * np.log10(np.abs(X) ** 2)).max() < 1e-3
+    assert abs(f[np.argmax(y)] - 0.12 * 2.0e6) < 2.0e6 / 3000      # the carrier is where it was put
+    f, y = orc.getWelch(1.0, x, sizeFFT=256)
+    seg = x[: (n // 256) * 256].reshape(-1, 256).astype(np.complex128)
+    S = (np.abs(np.fft.fft(seg, axis=1)) ** 2).sum(axis=0)
+    assert np.abs(y - 10 * np.log10(np.fft.fftshift(S))).max() < 1e-3
+    t, f, s = orc.getWaterfall(1.0, x, sizeFFT=256)
+    assert s.dtype == np.float64 and s.shape == (256, n // 256) and np.allclose(t, np.arange(n // 256) * 256.0)
+    ref = np.fft.fftshift(np.abs(np.fft.fft(seg, axis=1)) ** 2, axes=1).T
+    assert np.abs(s - ref).max() <= 2e-6 * ref.max()
