@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libtempest_b200.so")
+# TEMPEST_B200_LIB (also read by the Julia wrapper) points at another build of the library, e.g. for A/B timing
+SO = os.environ.get("TEMPEST_B200_LIB") or os.path.join(HERE, "libtempest_b200.so")
 
 TSDR_CHAIN_PUBLISH_ALL = 1
 TSDR_CHAIN_NO_ALIGN = 2

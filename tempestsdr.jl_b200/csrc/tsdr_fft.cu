@@ -669,12 +669,12 @@ int tsdr_autocorr_plan_exec(tsdr_autocorr_plan* p, const float* x_dev, size_t in
     else { fp.out = out_dev; fp.m_lo = (int64_t)index_min - 1; fp.m_hi = (int64_t)index_max - 1; fp.raw = 0; }
     cudaStream_t st = p->stream;
     if (p->has_fft3 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 && !getenv("TSDR_FFT_TWO_LEVEL")) {
-        if (p->n == p->N) p->f3.p1<<<p->f3.grid_p1, kFastThreads, p->f3.smem_p1, st>>>(fp);
-        else p->f3.p1_padded<<<p->f3.grid_p1, kFastThreads, p->f3.smem_p1, st>>>(fp);
-        p->f3.p2<<<p->f3.grid_p2, kFastThreads, p->f3.smem_p2, st>>>(fp);
-        p->f3.p3<<<p->f3.grid_p3, kFastThreads, p->f3.smem_p3, st>>>(fp);
-        p->f3.p4<<<p->f3.grid_p2, kFastThreads, p->f3.smem_p2, st>>>(fp);
-        p->f3.p5<<<p->f3.grid_p1, kFastThreads, p->f3.smem_p1, st>>>(fp);
+        if (p->n == p->N) p->f3.p1<<<p->f3.grid_p1, p->f3.threads, p->f3.smem_p1, st>>>(fp);
+        else p->f3.p1_padded<<<p->f3.grid_p1, p->f3.threads, p->f3.smem_p1, st>>>(fp);
+        p->f3.p2<<<p->f3.grid_p2, p->f3.threads, p->f3.smem_p2, st>>>(fp);
+        p->f3.p3<<<p->f3.grid_p3, p->f3.threads, p->f3.smem_p3, st>>>(fp);
+        p->f3.p4<<<p->f3.grid_p2, p->f3.threads, p->f3.smem_p2, st>>>(fp);
+        p->f3.p5<<<p->f3.grid_p1, p->f3.threads, p->f3.smem_p1, st>>>(fp);
         p->launches += 2;
     } else if (p->has_fast && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) {
         const int grid_cols = fp.B >> p->fast.logc;

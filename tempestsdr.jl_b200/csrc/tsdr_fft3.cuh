@@ -21,7 +21,7 @@
 
 namespace tsdr {
 
-template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB>
+template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB, int LOGNT>
 struct Fft3 {
     static constexpr int NA = 1 << LOGNA, NB = 1 << LOGNB, NC = 1 << LOGNC;
     static constexpr int LOGNBC = LOGNB + LOGNC;
@@ -40,23 +40,23 @@ struct Fft3 {
 
 // W_len^k, k in [0, len), copied from the plan's longer table into shared memory: the butterflies'
 // twiddle reads then are LDS instead of global loads in the middle of every dependent chain
-template <int LOGLEN, int LOGTAB>
+template <int LOGLEN, int LOGTAB, int NT>
 __device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* __restrict__ tab, int tid) {
-    for (int k = tid; k < (1 << LOGLEN); k += kFastThreads) tw_s[k] = __ldg(tab + ((size_t)k << (LOGTAB - LOGLEN)));
+    for (int k = tid; k < (1 << LOGLEN); k += NT) tw_s[k] = __ldg(tab + ((size_t)k << (LOGTAB - LOGLEN)));
 }
 
 // ------------------------------------------------------------------------------- P1 --
 template <class F, bool PADDED>
-__global__ void __launch_bounds__(kFastThreads, 3) k3_p1(FftParams p) {
+__global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p1(FftParams p) {
     extern __shared__ __align__(16) float2 sm[];
     constexpr int LOGC = F::LOGC1_v, C = 1 << LOGC, HALF = C / 2, NA = F::NA_v;
     __shared__ float2 tw_s[NA];
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x << LOGC;
     const ColLayoutCt<LOGC> lay;
-    load_twiddles<F::LOGNA_v, F::LOGTAB_v>(tw_s, p.twB, tid);
+    load_twiddles<F::LOGNA_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
 #pragma unroll
-    for (int e = tid; e < NA * HALF; e += kFastThreads) {
+    for (int e = tid; e < NA * HALF; e += F::NT_v) {
         const int a = e / HALF, c2 = (e - a * HALF) * 2;
         const int64_t j = ((int64_t)a << F::LOGNBC_v) + r0 + c2;
         float4 v;
@@ -70,9 +70,9 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p1(FftParams p) {
         *reinterpret_cast<float4*>(&sm[lay(c2, a)]) = v;
     }
     __syncthreads();
-    fft_fwd_ct<F::LOGNA_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGNA_v>(sm, lay, tw_s, tid);
+    fft_fwd_ct<F::LOGNA_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGNA_v, F::NT_v>(sm, lay, tw_s, tid);
 #pragma unroll 4
-    for (int e = tid; e < NA * HALF; e += kFastThreads) {
+    for (int e = tid; e < NA * HALF; e += F::NT_v) {
         const int rho = e / HALF, c2 = (e - rho * HALF) * 2;
         const int ka = digit_rev_ct<F::LOGNA_v>(rho);
         const int r = r0 + c2;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p1(FftParams p) {
 
 // --------------------------------------------------------------------------- P2 / P4 --
 template <class F, int DIR>
-__global__ void __launch_bounds__(kFastThreads, 3) k3_p24(FftParams p) {
+__global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
     extern __shared__ __align__(16) float2 sm[];
     constexpr int LOGC = F::LOGC2_v, C = 1 << LOGC, HALF = C / 2, NB = F::NB_v;
     const int tid = threadIdx.x;
@@ -95,18 +95,18 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p24(FftParams p) {
     const ColLayoutCt<LOGC> lay;
     float4* T4 = reinterpret_cast<float4*>(p.T);
     __shared__ float2 tw_s[NB];
-    load_twiddles<F::LOGNB_v, F::LOGTAB_v>(tw_s, p.twB, tid);
+    load_twiddles<F::LOGNB_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
 #pragma unroll
-    for (int e = tid; e < NB * HALF; e += kFastThreads) {
+    for (int e = tid; e < NB * HALF; e += F::NT_v) {
         const int i = e / HALF, c2 = (e - i * HALF) * 2;   // forward: i = b ; inverse: i = kb
         const int pos = DIR > 0 ? i : digit_pos_ct<F::LOGNB_v>(i);
         *reinterpret_cast<float4*>(&sm[lay(c2, pos)]) = T4[(base + ((int64_t)i << F::LOGNC_v) + c2) >> 1];
     }
     __syncthreads();
-    if (DIR > 0) fft_fwd_ct<F::LOGNB_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGNB_v>(sm, lay, tw_s, tid);
-    else fft_inv_ct<F::LOGNB_v, CtPlan<F::LOGNB_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGNB_v>(sm, lay, tw_s, tid);
+    if (DIR > 0) fft_fwd_ct<F::LOGNB_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGNB_v, F::NT_v>(sm, lay, tw_s, tid);
+    else fft_inv_ct<F::LOGNB_v, CtPlan<F::LOGNB_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGNB_v, F::NT_v>(sm, lay, tw_s, tid);
 #pragma unroll 4
-    for (int e = tid; e < NB * HALF; e += kFastThreads) {
+    for (int e = tid; e < NB * HALF; e += F::NT_v) {
         const int pos = e / HALF, c2 = (e - pos * HALF) * 2;
         const int c = c0 + c2;
         const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, pos)]);
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p24(FftParams p) {
 
 // ------------------------------------------------------------------------------- P3 --
 template <class F>
-__global__ void __launch_bounds__(kFastThreads, 3) k3_p3(FftParams p) {
+__global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
     extern __shared__ __align__(16) float2 sm[];
     constexpr int NA = F::NA_v, NB = F::NB_v, NC = F::NC_v, R = F::R_v, LOGNC = F::LOGNC_v, LOGNB = F::LOGNB_v, LOGNA = F::LOGNA_v;
     const int tid = threadIdx.x;
@@ -137,13 +137,13 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p3(FftParams p) {
     const RowLayoutCt lay{F::kRowStride_v};
     float4* T4 = reinterpret_cast<float4*>(p.T);
     __shared__ float2 tw_s[NC];
-    load_twiddles<LOGNC, F::LOGTAB_v>(tw_s, p.twB, tid);
+    load_twiddles<LOGNC, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
     // slot s in [0, R): rows (rowA, rowB); smem row s holds rowA, smem row R + s holds rowB
     auto rowA_of = [&](int s) { return special ? t0 + s : NB + t0 + s; };
     auto rowB_of = [&](int s) { return special ? ((NB - (t0 + s)) & (NB - 1)) : NA * NB - 1 - (t0 + s); };
     auto valid = [&](int s) { return !special || t0 + s <= NB / 2; };
 #pragma unroll
-    for (int e = tid; e < 2 * R * (NC / 2); e += kFastThreads) {
+    for (int e = tid; e < 2 * R * (NC / 2); e += F::NT_v) {
         const int srow = e / (NC / 2), i2 = (e - srow * (NC / 2)) * 2;
         const int s = srow & (R - 1);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -155,9 +155,9 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p3(FftParams p) {
         sm[lay(srow, i2 + 1)] = make_float2(v.z, v.w);
     }
     __syncthreads();
-    fft_fwd_ct<LOGNC, 0, false, F::LOGR_v + 1, RowLayoutCt, LOGNC>(sm, lay, tw_s, tid);
+    fft_fwd_ct<LOGNC, 0, false, F::LOGR_v + 1, RowLayoutCt, LOGNC, F::NT_v>(sm, lay, tw_s, tid);
     const float sc = 0.5f * p.inv_scale;
-    for (int e = tid; e < R * NC; e += kFastThreads) {
+    for (int e = tid; e < R * NC; e += F::NT_v) {
         const int s = e >> LOGNC, kc = e & (NC - 1);
         if (!valid(s)) continue;
         const int rowA = rowA_of(s), rowB = rowB_of(s);
@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p3(FftParams p) {
         }
     }
     __syncthreads();
-    fft_inv_ct<LOGNC, CtPlan<LOGNC>::nst - 1, false, F::LOGR_v + 1, RowLayoutCt, LOGNC>(sm, lay, tw_s, tid);
+    fft_inv_ct<LOGNC, CtPlan<LOGNC>::nst - 1, false, F::LOGR_v + 1, RowLayoutCt, LOGNC, F::NT_v>(sm, lay, tw_s, tid);
     // undo the stage-2 twiddle W_M'^(kb c) and write the rows back in place
-    for (int e = tid; e < 2 * R * (NC / 2); e += kFastThreads) {
+    for (int e = tid; e < 2 * R * (NC / 2); e += F::NT_v) {
         const int srow = e / (NC / 2), c2 = (e - srow * (NC / 2)) * 2;
         const int s = srow & (R - 1);
         if (!valid(s)) continue;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p3(FftParams p) {
 
 // ------------------------------------------------------------------------------- P5 --
 template <class F>
-__global__ void __launch_bounds__(kFastThreads, 3) k3_p5(FftParams p) {
+__global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p5(FftParams p) {
     extern __shared__ __align__(16) float2 sm[];
     constexpr int LOGC = F::LOGC1_v, C = 1 << LOGC, HALF = C / 2, NA = F::NA_v;
     const int tid = threadIdx.x;
@@ -211,17 +211,17 @@ __global__ void __launch_bounds__(kFastThreads, 3) k3_p5(FftParams p) {
     const ColLayoutCt<LOGC> lay;
     const float4* T4 = reinterpret_cast<const float4*>(p.T);
     __shared__ float2 tw_s[NA];
-    load_twiddles<F::LOGNA_v, F::LOGTAB_v>(tw_s, p.twB, tid);
+    load_twiddles<F::LOGNA_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
 #pragma unroll
-    for (int e = tid; e < NA * HALF; e += kFastThreads) {
+    for (int e = tid; e < NA * HALF; e += F::NT_v) {
         const int ka = e / HALF, c2 = (e - ka * HALF) * 2;
         *reinterpret_cast<float4*>(&sm[lay(c2, digit_pos_ct<F::LOGNA_v>(ka))]) = T4[(((int64_t)ka << F::LOGNBC_v) + r0 + c2) >> 1];
     }
     __syncthreads();
-    fft_inv_ct<F::LOGNA_v, CtPlan<F::LOGNA_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGNA_v>(sm, lay, tw_s, tid);
+    fft_inv_ct<F::LOGNA_v, CtPlan<F::LOGNA_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGNA_v, F::NT_v>(sm, lay, tw_s, tid);
     const bool out_aligned = (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
 #pragma unroll 4
-    for (int e = tid; e < NA * HALF; e += kFastThreads) {
+    for (int e = tid; e < NA * HALF; e += F::NT_v) {
         const int a = e / HALF, c2 = (e - a * HALF) * 2;
         const int64_t j = ((int64_t)a << F::LOGNBC_v) + r0 + c2;
         const int64_t m0 = 2 * j;   // y[j] = r[2j] + i r[2j+1]: two adjacent columns = four consecutive lags
@@ -253,27 +253,29 @@ struct Fft3Kernels {
     void (*p3)(FftParams);
     void (*p4)(FftParams);
     void (*p5)(FftParams);
-    int grid_p1, grid_p2, grid_p3;
+    int grid_p1, grid_p2, grid_p3, threads;
     size_t smem_p1, smem_p2, smem_p3;
 };
 
 // the kernels take the shape through a traits class with plain static members
-template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB>
+template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB, int LOGNT>
 struct Fft3Traits {
-    using G = Fft3<LOGNA, LOGNB, LOGNC, LOGC1, LOGC2, LOGR, LOGTAB>;
+    using G = Fft3<LOGNA, LOGNB, LOGNC, LOGC1, LOGC2, LOGR, LOGTAB, LOGNT>;
     static constexpr int LOGNA_v = LOGNA, LOGNB_v = LOGNB, LOGNC_v = LOGNC, LOGC1_v = LOGC1, LOGC2_v = LOGC2, LOGR_v = LOGR,
                          LOGTAB_v = LOGTAB, LOGNBC_v = LOGNB + LOGNC, NA_v = 1 << LOGNA, NB_v = 1 << LOGNB, NC_v = 1 << LOGNC,
-                         R_v = 1 << LOGR, kRowStride_v = G::kRowStride, n_regular_v = G::n_regular;
+                         R_v = 1 << LOGR, kRowStride_v = G::kRowStride, n_regular_v = G::n_regular, NT_v = 1 << LOGNT,
+                         MINB_v = (3 * kFastThreads) >> LOGNT;
 };
 
-template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB>
+template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB, int LOGNT>
 static Fft3Kernels make_fft3() {
-    using F = Fft3Traits<LOGNA, LOGNB, LOGNC, LOGC1, LOGC2, LOGR, LOGTAB>;
+    using F = Fft3Traits<LOGNA, LOGNB, LOGNC, LOGC1, LOGC2, LOGR, LOGTAB, LOGNT>;
     using G = typename F::G;
     Fft3Kernels k;
     k.p1 = k3_p1<F, false>; k.p1_padded = k3_p1<F, true>;
     k.p2 = k3_p24<F, +1>; k.p4 = k3_p24<F, -1>;
     k.p3 = k3_p3<F>; k.p5 = k3_p5<F>;
+    k.threads = F::NT_v;
     k.grid_p1 = G::grid_p1; k.grid_p2 = G::grid_p2; k.grid_p3 = G::grid_p3;
     k.smem_p1 = G::smem_p1; k.smem_p2 = G::smem_p2; k.smem_p3 = G::smem_p3;
     return k;
@@ -282,11 +284,18 @@ static Fft3Kernels make_fft3() {
 // shapes with a three-level build, keyed by log2 of the transform length N (real samples) and of
 // the two-level B table length (the W_B^k table the plan already owns, reused with a stride)
 static bool find_fft3(int logN, int logtab, Fft3Kernels* out) {
-#define TSDR_FFT3(n, a, b, c, c1, c2, r, tab) if (logN == n && logtab == tab) { *out = make_fft3<a, b, c, c1, c2, r, tab>(); return true; }
-    // measured on B200 (tools/run_autocorr.py): the three-level split wins at 2^24 (0.283 vs 0.306 ms) and
-    // 2^26 (1.35 vs 1.47 ms); at 2^22, 2^23 and 2^25 the two-level kernels are a few percent faster.
-    TSDR_FFT3(24, 8, 8, 7, 5, 5, 5, 12)   // M = 2^23: the benchmark size
-    TSDR_FFT3(26, 9, 8, 8, 4, 5, 4, 13)   // M = 2^25
+#define TSDR_FFT3(n, a, b, c, c1, c2, r, tab, nt) if (logN == n && logtab == tab) { *out = make_fft3<a, b, c, c1, c2, r, tab, nt>(); return true; }
+    // Shapes measured on B200 (tools/fft_variants.py).  Tiles of 16 columns (128-byte row pieces, 32 KB of shared
+    // memory) and 8 row pairs beat the 32-column / 32-pair tiles of the first version by 16-27 %: the per-CTA
+    // load -> transform -> store sequence is latency bound, and twice as many half-sized CTAs overlap it better
+    // and leave a shorter tail; 8-column tiles (64-byte pieces) lose again.  Against the two-level kernels:
+    // 2^23 0.122 vs 0.145 ms, 2^24 0.223 vs 0.306, 2^25 0.450 vs 0.614, 2^26 1.06 vs 1.45; at 2^22 the two-level
+    // kernels stay (0.072 ms both).  CTAs of 128 threads on the same tiles (two butterflies per thread and stage,
+    // six CTAs per SM) are 10-16 % slower than 256 threads; min-blocks 4 or 5 (64 / 48 registers) do not help either.
+    TSDR_FFT3(23, 8, 7, 7, 4, 4, 3, 12, 8)   // M = 2^22: what the GUI's 3e6 / 4e6-sample calls pad to
+    TSDR_FFT3(24, 8, 7, 8, 4, 4, 3, 12, 8)   // M = 2^23: the benchmark size
+    TSDR_FFT3(25, 8, 8, 8, 4, 4, 3, 13, 8)   // M = 2^24
+    TSDR_FFT3(26, 9, 8, 8, 4, 4, 3, 13, 8)   // M = 2^25
 #undef TSDR_FFT3
     return false;
 }

@@ -57,7 +57,7 @@ template <int LOGC> struct ColLayoutCt {  // 2^LOGC interleaved transforms, 4 pa
 template <int LOGC> __host__ __device__ constexpr int col_padded_ct(int total) { return total + ((total >> 6) << 2) + 4; }
 
 // tw = table of W_(2^LOGTAB)^k; LOGTAB >= LOGLEN (a longer table is read with a larger stride)
-template <int LOGLEN, int LOGR, int LOGLCUR, int DIR, bool COLFAST, int LOGNB, int LOGTAB, class Layout>
+template <int LOGLEN, int LOGR, int LOGLCUR, int DIR, bool COLFAST, int LOGNB, int LOGTAB, int NT, class Layout>
 __device__ __forceinline__ void stage_ct(float2* s, const Layout lay, const float2* __restrict__ tw, int tid) {
     constexpr int R = 1 << LOGR;
     constexpr int LOGSUB = LOGLCUR - LOGR;
@@ -65,9 +65,9 @@ __device__ __forceinline__ void stage_ct(float2* s, const Layout lay, const floa
     constexpr int TOTAL = 1 << (LOGNB + LOGPER);
     constexpr int TWSHIFT = LOGTAB - LOGLCUR;
 #pragma unroll 1
-    for (int e0 = 0; e0 < TOTAL; e0 += kFastThreads) {
+    for (int e0 = 0; e0 < TOTAL; e0 += NT) {
         const int e = e0 + tid;
-        if (TOTAL < kFastThreads && e >= TOTAL) break;
+        if (TOTAL < NT && e >= TOTAL) break;
         int b, w;
         if (COLFAST) { b = e & ((1 << LOGNB) - 1); w = e >> LOGNB; }
         else { b = e >> LOGPER; w = e & ((1 << LOGPER) - 1); }
@@ -101,20 +101,20 @@ __device__ __forceinline__ void stage_ct(float2* s, const Layout lay, const floa
     }
 }
 
-template <int LOGLEN, int STAGE, bool COLFAST, int LOGNB, class Layout, int LOGTAB = LOGLEN>
+template <int LOGLEN, int STAGE, bool COLFAST, int LOGNB, class Layout, int LOGTAB = LOGLEN, int NT = kFastThreads>
 __device__ __forceinline__ void fft_fwd_ct(float2* s, const Layout lay, const float2* __restrict__ tw, int tid) {
     if constexpr (STAGE < CtPlan<LOGLEN>::nst) {
-        stage_ct<LOGLEN, CtPlan<LOGLEN>::logr(STAGE), CtPlan<LOGLEN>::loglcur(STAGE), +1, COLFAST, LOGNB, LOGTAB>(s, lay, tw, tid);
+        stage_ct<LOGLEN, CtPlan<LOGLEN>::logr(STAGE), CtPlan<LOGLEN>::loglcur(STAGE), +1, COLFAST, LOGNB, LOGTAB, NT>(s, lay, tw, tid);
         __syncthreads();
-        fft_fwd_ct<LOGLEN, STAGE + 1, COLFAST, LOGNB, Layout, LOGTAB>(s, lay, tw, tid);
+        fft_fwd_ct<LOGLEN, STAGE + 1, COLFAST, LOGNB, Layout, LOGTAB, NT>(s, lay, tw, tid);
     }
 }
-template <int LOGLEN, int STAGE, bool COLFAST, int LOGNB, class Layout, int LOGTAB = LOGLEN>
+template <int LOGLEN, int STAGE, bool COLFAST, int LOGNB, class Layout, int LOGTAB = LOGLEN, int NT = kFastThreads>
 __device__ __forceinline__ void fft_inv_ct(float2* s, const Layout lay, const float2* __restrict__ tw, int tid) {
     if constexpr (STAGE >= 0) {
-        stage_ct<LOGLEN, CtPlan<LOGLEN>::logr(STAGE), CtPlan<LOGLEN>::loglcur(STAGE), -1, COLFAST, LOGNB, LOGTAB>(s, lay, tw, tid);
+        stage_ct<LOGLEN, CtPlan<LOGLEN>::logr(STAGE), CtPlan<LOGLEN>::loglcur(STAGE), -1, COLFAST, LOGNB, LOGTAB, NT>(s, lay, tw, tid);
         __syncthreads();
-        fft_inv_ct<LOGLEN, STAGE - 1, COLFAST, LOGNB, Layout, LOGTAB>(s, lay, tw, tid);
+        fft_inv_ct<LOGLEN, STAGE - 1, COLFAST, LOGNB, Layout, LOGTAB, NT>(s, lay, tw, tid);
     }
 }
 
