@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p5(FftParams p) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 o[t] = o[t] * o[t];  // abs2 of the (real) correlation
-                if (p.log_scale) o[t] = 10.0f * log10f(o[t]);
+                if (p.log_scale) o[t] = db10_fast(o[t]);
             }
         }
         if (out_aligned && m0 >= p.m_lo && m0 + 3 <= p.m_hi && (((m0 - p.m_lo) & 3) == 0)) {

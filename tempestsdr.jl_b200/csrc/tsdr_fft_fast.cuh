@@ -10,6 +10,11 @@ namespace tsdr {
 
 constexpr int kFastThreads = 256;
 
+// 10 log10(x) as 10 log10(2) * lg2.approx(x): one MUFU instead of the ~20-instruction log10f (a quarter of the
+// last pass's instructions).  Absolute error <= 3.01 * 2^-22 = 7e-7 dB, four orders below the 1e-2 dB tolerance
+// the Float32 FFT itself needs; 0 -> -Inf, Inf -> Inf, NaN -> NaN and subnormal inputs behave like log10f.
+__device__ __forceinline__ float db10_fast(float x) { return 3.01029995663981195f * __log2f(x); }
+
 // radix plan of a 2^LOGLEN transform: first stage 2^(LOGLEN % 4) when non-zero, then radix 16
 template <int LOGLEN> struct CtPlan {
     static constexpr int rem = LOGLEN % 4;
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) k_ifft_cols_ct(FftParams p) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 o[t] = o[t] * o[t];  // abs2 of the (real) correlation
-                if (p.log_scale) o[t] = 10.0f * log10f(o[t]);
+                if (p.log_scale) o[t] = db10_fast(o[t]);
             }
         }
         if (m0 >= p.m_lo && m0 + 3 <= p.m_hi && (((m0 - p.m_lo) & 3) == 0) && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
