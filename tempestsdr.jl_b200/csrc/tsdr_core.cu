@@ -882,6 +882,8 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
     if (e == cudaSuccess) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        // highest priority: the sync search and accumulate of buffer b must not be starved by the render of
+        // buffer b+1, whose successor waits for them (same priority as the primary stream: +15 % step time)
         e = cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, hi);
     }
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {

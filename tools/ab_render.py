@@ -41,6 +41,11 @@ def run(so, name):
         L.tsdr_chain_destroy(h)
     return step * 1e3, ms[0] / p[0] * 1e3
 sos = sys.argv[1:]
+envs = os.environ.get("AB_ENVS", "").split(";")   # e.g. AB_ENVS="TSDR_X=1;TSDR_X=2": each build is run under each setting
 for rep in range(3):
     for name in WL:
-        print(rep, name, "  ".join("%s: step %.1f us render %.1f us" % ((os.path.basename(s),) + run(s, name)) for s in sos), flush=True)
+        for ev in envs:
+            if ev:
+                k, v = ev.split("=")
+                os.environ[k] = v
+            print(rep, name, ev, "  ".join("%s: step %.1f us render %.1f us" % ((os.path.basename(s),) + run(s, name)) for s in sos), flush=True)
