@@ -145,7 +145,7 @@ def run_reference(args, wl, rank):
            "cpu_baseline": {"value": val, "unit": "MS/s", "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def bench_autocorr(tsdr, torch, dev, hbm_peak):
@@ -278,7 +278,30 @@ def int16_ingest_measure(tsdr, torch, ch, ring, wl, S, frames, steps, warmup):
                     "d2h_bytes_per_step": R * 4, "steps": k}}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """stdout carries exactly one JSON line: everything else libraries print there (NCCL's version banner, torchrun
+    notices) is sent to stderr; emit() writes the line to the real stdout"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if _REAL_STDOUT is not None:
+        _REAL_STDOUT.write(line + "\n")
+        _REAL_STDOUT.flush()
+    else:
+        print(line, flush=True)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -467,7 +490,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
 
 
 if __name__ == "__main__":

@@ -61,6 +61,7 @@ def _load():
         "orc_chain_buffer": (C.c_int, [_f32p, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_double, C.c_float,
                                        C.POINTER(_Sync), _f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
         "orc_num_threads": (C.c_int, []),
+        "orc_openmp": (C.c_int, []),
         "orc_upsampler_create": (C.c_void_p, [C.c_size_t, C.c_int]),
         "orc_upsampler_H": (None, [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")]),
         "orc_upsampler_apply": (C.c_int, [C.c_void_p, _f32p, _f32p]),
@@ -350,4 +351,11 @@ def chain_buffer(iq, Fs, x_t, y_t, fv, alpha, sync, image_out, publish=True, nth
 
 
 def num_threads():
-    return lib.orc_num_threads()
+    """threads orc_chain_buffer can use: every core this process may run on when the library has OpenMP
+    (launchers such as torchrun export OMP_NUM_THREADS=1, which the explicit nthreads argument overrides)"""
+    if not lib.orc_openmp():
+        return 1
+    try:
+        return max(lib.orc_num_threads(), len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(lib.orc_num_threads(), os.cpu_count() or 1)

@@ -45,6 +45,14 @@ int orc_fft_z2z(const double* in, double* out, size_t n, int inverse) {
     return orcd_c2c((const orc_cd*)in, (orc_cd*)out, n, inverse);
 }
 
+int orc_openmp(void) {
+#ifdef _OPENMP
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

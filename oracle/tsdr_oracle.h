@@ -96,6 +96,8 @@ int orc_chain_buffer(const float* iq, size_t nEch, double Fs, int x_t, int y_t, 
 /* Same arithmetic but without publishing: returns only the final image_out.  */
 
 int orc_num_threads(void);
+/* 1 when the library was built with OpenMP (orc_chain_buffer then honours its nthreads argument) */
+int orc_openmp(void);
 
 #ifdef __cplusplus
 }
