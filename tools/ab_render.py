@@ -20,7 +20,7 @@ def run(so, name):
     with torch.cuda.stream(st):
         h = C.c_void_p()
         L.tsdr_chain_create.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_float, C.c_size_t, C.c_int, C.c_void_p]
-        assert L.tsdr_chain_create(C.byref(h), 0, Fs, x, y, fv, 0.1, n, 0, C.c_void_p(st.cuda_stream)) == 0
+        assert L.tsdr_chain_create(C.byref(h), 0, Fs, x, y, fv, 0.1, n, int(os.environ.get("AB_FLAGS", "0")), C.c_void_p(st.cuda_stream)) == 0
         L.tsdr_chain_push_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.tsdr_chain_flush.argtypes = [C.c_void_p]; L.tsdr_chain_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.tsdr_chain_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]; L.tsdr_chain_destroy.argtypes = [C.c_void_p]
@@ -39,7 +39,7 @@ def run(so, name):
         L.tsdr_chain_kernel_times(h, ms, p)
         L.tsdr_chain_set_profiling(h, 0)
         L.tsdr_chain_destroy(h)
-    return step * 1e3, ms[0] / p[0] * 1e3
+    return step * 1e3, ms[0] / p[0] * 1e3, ms[1] / p[0] * 1e3
 sos = sys.argv[1:]
 envs = os.environ.get("AB_ENVS", "").split(";")   # e.g. AB_ENVS="TSDR_X=1;TSDR_X=2": each build is run under each setting
 for rep in range(3):
@@ -48,4 +48,4 @@ for rep in range(3):
             if ev:
                 k, v = ev.split("=")
                 os.environ[k] = v
-            print(rep, name, ev, "  ".join("%s: step %.1f us render %.1f us" % ((os.path.basename(s),) + run(s, name)) for s in sos), flush=True)
+            print(rep, name, ev, "  ".join("%s: step %.1f render %.1f sync %.1f us" % ((os.path.basename(s),) + run(s, name)) for s in sos), flush=True)
