@@ -70,5 +70,43 @@ def main():
     print("wrote golden_v1.npz:", {k: v.shape for k, v in out.items()})
 
 
+def int16_inputs():
+    """the chain case quantised to Int16 pairs, as a `:short` recording stores it (src/DatBinaryFiles.jl:47-49)"""
+    iq = chain_inputs()
+    return np.stack([np.rint(iq.real * 6000.0), np.rint(iq.imag * 6000.0)], axis=1).astype(np.int16)
+
+
+def spectrum_input():
+    rng = np.random.default_rng(0xB201)
+    n = 1500
+    x = (rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64)
+    return x + (5.0 * np.exp(2j * np.pi * 0.3125 * np.arange(n))).astype(np.complex64)
+
+
+def main_v2():
+    """golden_v2.npz: the rows added after v1 -- Int16 ingest and the GetSpectrum.jl functions"""
+    out = {}
+    i16 = int16_inputs()
+    wide = (i16[:, 0].astype(np.float32) + 1j * i16[:, 1].astype(np.float32)).astype(np.complex64)
+    c = CHAIN_CASE
+    so = orc.SyncXY()
+    acc, _, sy, sx = orc.chain_buffer(wide, c["Fs"], c["x_t"], c["y_t"], c["fv"], c["alpha"], so,
+                                      np.zeros((600, 800), np.float32), publish=False)
+    out["i16_chain_sy"], out["i16_chain_sx"] = sy, sx
+    acc = np.ascontiguousarray(acc, np.float32)
+    out["i16_chain_image_sha256"] = np.frombuffer(hashlib.sha256(acc.tobytes()).digest(), np.uint8).copy()
+    out["i16_chain_image_sub"] = acc[::37, ::41].copy()
+    x = spectrum_input()
+    out["spectrum_in"] = x
+    out["getSpectrum_1000"] = orc.getSpectrum(1.0, x, N=1000)[1]     # chirp-z route on the GPU
+    out["getSpectrum_1024"] = orc.getSpectrum(1.0, x, N=1024)[1]     # direct power-of-two route
+    out["getWelch_256"] = orc.getWelch(1.0, x, sizeFFT=256)[1]
+    out["getWaterfall_64"] = orc.getWaterfall(1.0, x, sizeFFT=64)[2].astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "golden_v2.npz"), **out)
+    print("wrote golden_v2.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--v1" in sys.argv:
+        main()
+    main_v2()

@@ -510,6 +510,38 @@ def test_gpu_matches_committed_goldens():
     assert np.max(np.abs(got - G["autocorr_db"])) <= 1e-2
 
 
+def test_gpu_matches_committed_goldens_v2():
+    # golden_v2.npz: Int16 ingest (bit-exact) and the GetSpectrum.jl functions (Float32 FFT tolerance)
+    import hashlib
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    G2 = np.load(os.path.join(here, "golden", "golden_v2.npz"))
+    sha = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, np.float32).tobytes()).digest(), np.uint8)
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    c = mg.CHAIN_CASE
+    i16 = mg.int16_inputs()
+    ch = tsdr.Chain(c["Fs"], tsdr.VideoMode(c["x_t"], c["y_t"], c["fv"]), alpha=c["alpha"], max_samples=i16.shape[0])
+    assert ch.push_i16(i16) == c["frames"]
+    sy, sx = ch.offsets()
+    assert np.array_equal(sy, G2["i16_chain_sy"]) and np.array_equal(sx, G2["i16_chain_sx"])
+    assert np.array_equal(sha(ch.image()), G2["i16_chain_image_sha256"])
+    ch.close()
+    x = G2["spectrum_in"]
+
+    def close_db(y, ref, tol):
+        strong = ref > ref.max() - 60
+        return np.abs(y[strong] - ref[strong]).max() < tol and int(np.argmax(y)) == int(np.argmax(ref))
+
+    assert close_db(tsdr.getSpectrum(1.0, x, N=1000)[1], G2["getSpectrum_1000"], 2e-2)
+    assert close_db(tsdr.getSpectrum(1.0, x, N=1024)[1], G2["getSpectrum_1024"], 1e-2)
+    assert close_db(tsdr.getWelch(1.0, x, sizeFFT=256)[1], G2["getWelch_256"], 1e-2)
+    s = tsdr.getWaterfall(1.0, x, sizeFFT=64)[2]
+    assert np.abs(s - G2["getWaterfall_64"]).max() <= 5e-6 * G2["getWaterfall_64"].max()
+
+
 def test_findmax_device_and_hypothesis_sweep(synth):
     import torch
     Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)

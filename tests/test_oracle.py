@@ -184,6 +184,27 @@ def test_oracle_chain_reproduces_golden(synth):
     assert np.array_equal(_sha(so.beta_x()), GOLD["chain_beta_x_last_sha256"])
 
 
+def test_oracle_reproduces_goldens_v2():
+    G2 = np.load(os.path.join(HERE, "golden", "golden_v2.npz"))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    c = mg.CHAIN_CASE
+    i16 = mg.int16_inputs()
+    wide = (i16[:, 0].astype(np.float32) + 1j * i16[:, 1].astype(np.float32)).astype(np.complex64)
+    so = orc.SyncXY()
+    acc, _, sy, sx = orc.chain_buffer(wide, c["Fs"], c["x_t"], c["y_t"], c["fv"], c["alpha"], so,
+                                      np.zeros((600, 800), np.float32), publish=False)
+    assert np.array_equal(sy, G2["i16_chain_sy"]) and np.array_equal(sx, G2["i16_chain_sx"])
+    assert np.array_equal(_sha(acc), G2["i16_chain_image_sha256"])
+    x = G2["spectrum_in"]
+    assert np.array_equal(x, mg.spectrum_input())
+    assert np.array_equal(orc.getSpectrum(1.0, x, N=1000)[1], G2["getSpectrum_1000"])
+    assert np.array_equal(orc.getSpectrum(1.0, x, N=1024)[1], G2["getSpectrum_1024"])
+    assert np.array_equal(orc.getWelch(1.0, x, sizeFFT=256)[1], G2["getWelch_256"])
+    assert np.array_equal(orc.getWaterfall(1.0, x, sizeFFT=64)[2].astype(np.float32), G2["getWaterfall_64"])
+
+
 def test_get_spectrum_family_against_numpy():
     # src/GetSpectrum.jl:21-66 restated on the oracle's own FFT, checked here against numpy's double FFT
     rng = np.random.default_rng(21)
