@@ -633,7 +633,8 @@ int tsdr_autocorr_plan_create(tsdr_autocorr_plan** out, int device, size_t n, vo
         while ((1 << logb) < B) ++logb;
         int logN = 0;
         while (((size_t)1 << logN) < p->N) ++logN;
-        p->has_fft3 = find_fft3(logN, logb, &p->f3);
+        // TSDR_FFT_TWO_LEVEL=1 (read once, here) keeps a plan on the two-level kernels: tools/fft_variants.py times both
+        p->has_fft3 = !getenv("TSDR_FFT_TWO_LEVEL") && find_fft3(logN, logb, &p->f3);
         if (p->has_fft3 && e == cudaSuccess) {
             e = cudaFuncSetAttribute(p->f3.p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p1);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p1_padded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p1);
@@ -668,7 +669,7 @@ int tsdr_autocorr_plan_exec(tsdr_autocorr_plan* p, const float* x_dev, size_t in
     if (p->fold) { fp.out = p->d_lin; fp.m_lo = 0; fp.m_hi = (int64_t)p->n; fp.raw = 1; }
     else { fp.out = out_dev; fp.m_lo = (int64_t)index_min - 1; fp.m_hi = (int64_t)index_max - 1; fp.raw = 0; }
     cudaStream_t st = p->stream;
-    if (p->has_fft3 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 && !getenv("TSDR_FFT_TWO_LEVEL")) {
+    if (p->has_fft3 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) {
         if (p->n == p->N) p->f3.p1<<<p->f3.grid_p1, p->f3.threads, p->f3.smem_p1, st>>>(fp);
         else p->f3.p1_padded<<<p->f3.grid_p1, p->f3.threads, p->f3.smem_p1, st>>>(fp);
         p->f3.p2<<<p->f3.grid_p2, p->f3.threads, p->f3.smem_p2, st>>>(fp);
