@@ -162,6 +162,7 @@ int tsdr_chain_push_ring(tsdr_chain* c, tsdr_ring* r, int sample_format, int tim
  * integrates frames k..k+F-1 of a long capture primes its chain with frame k-1 so that its
  * first s_y equals the one of the sequential run. */
 int tsdr_chain_prime_host(tsdr_chain* c, const float* iq_host, size_t n);
+int tsdr_chain_prime_device(tsdr_chain* c, const float* iq_dev, size_t n);
 int tsdr_chain_sync(tsdr_chain* c);
 /* Make the primary stream wait (on the device, no host block) for the work the chain queued
  * on its internal auxiliary stream: after this, an event recorded on the primary stream

@@ -60,6 +60,7 @@ SIGNATURES = {
     "tsdr_chain_push_host_deliver": (C.c_int, [_vp, _vp, C.c_size_t, _ip, _vp]),
     "tsdr_chain_wait_delivery": (C.c_int, [_vp, C.c_int]),
     "tsdr_chain_prime_host": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "tsdr_chain_prime_device": (C.c_int, [_vp, _vp, C.c_size_t]),
     "tsdr_chain_sync": (C.c_int, [_vp]),
     "tsdr_chain_flush": (C.c_int, [_vp]),
     "tsdr_chain_read_image": (C.c_int, [_vp, _vp]),

@@ -353,6 +353,10 @@ class Chain:
         check(_lib.load().tsdr_chain_prime_host(self._h, _ptr(z), n))
         self._keep = [z] + list(getattr(self, "_keep", []))[:1]
 
+    def prime_device(self, ptr, n):
+        """prime() for samples already in device memory"""
+        check(_lib.load().tsdr_chain_prime_device(self._h, C.c_void_p(ptr), int(n)))
+
     def push_host_ptr(self, ptr, n):
         nf = C.c_int(0)
         check(_lib.load().tsdr_chain_push_host(self._h, C.c_void_p(ptr), int(n), C.byref(nf)))

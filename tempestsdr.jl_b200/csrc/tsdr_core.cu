@@ -1074,6 +1074,14 @@ int tsdr_chain_prime_host(tsdr_chain* c, const float* iq_host, size_t n) {
     return rc;
 }
 
+int tsdr_chain_prime_device(tsdr_chain* c, const float* iq_dev, size_t n) {
+    TSDR_REQUIRE(c && iq_dev, "NULL argument");
+    TSDR_REQUIRE((reinterpret_cast<uintptr_t>(iq_dev) & 7) == 0, "device buffer must be 8-byte aligned");
+    TSDR_REQUIRE(!(c->flags & TSDR_CHAIN_NO_ALIGN), "priming is meaningless without frame alignment");
+    TSDR_CUDA(cudaSetDevice(c->device));
+    return chain_run(c, iq_dev, n, nullptr, true);
+}
+
 int tsdr_chain_push_device(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames) {
     TSDR_REQUIRE(c && (iq_dev || n == 0), "NULL argument");
     TSDR_REQUIRE((reinterpret_cast<uintptr_t>(iq_dev) & 7) == 0, "device buffer must be 8-byte aligned");

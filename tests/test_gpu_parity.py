@@ -435,6 +435,17 @@ def test_block_integration_with_halo_matches_sequential(synth):
             ch.prime(iq[(k0 - 1) * S:k0 * S])
         assert ch.push(iq[k0 * S:k1 * S]) == k1 - k0
         sy, sx = ch.offsets()
+        if k0 > 0:   # the same block primed from device memory, then reset and reused: identical state
+            import torch
+            halo = torch.from_numpy(iq[(k0 - 1) * S:k0 * S].view(np.float32).copy()).cuda()
+            ch2 = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=alpha, max_samples=(k1 - k0) * S)
+            for _ in range(2):
+                ch2.reset()
+                ch2.prime_device(halo.data_ptr(), S)
+                ch2.push(iq[k0 * S:k1 * S])
+                sy2, sx2 = ch2.offsets()
+                assert np.array_equal(sy2, sy) and np.array_equal(sx2, sx) and np.array_equal(ch2.image(), ch.image())
+            ch2.close()
         sy_all += list(sy); sx_all += list(sx)
         total += ch.image().astype(np.float64) * parallel.ema_tail_weight(alpha, N - k1)
         ch.close()
