@@ -34,6 +34,11 @@ WORKLOADS = {
     "cfg5": dict(name="cfg5: 200 MS/s, VideoMode(4400,2250,30) 3840x2160@30, 1000-frame integration, "
                       "frame blocks per GPU + one all-reduce",
                  Fs=200e6, x_t=4400, y_t=2250, fv=30.0, n_ech=10 * 6_666_667, ring=2, total_frames=1000),
+    # BASELINE.json configs[3]: autocorrelation refresh-rate sweep over every refresh rate of allVideoConfigurations,
+    # 2^26-sample power buffers, one buffer per GPU per step (handled by run_sweep)
+    "cfg4": dict(name="cfg4: autocorrelation of 2^26 power samples (200 MS/s, 2560x1440@60 capture) + refresh-rate sweep "
+                      "over all VideoConfigurations hypotheses, one buffer per GPU",
+                 Fs=200e6, x_t=2720, y_t=1481, fv=60.0, n_ech=1 << 26, ring=2, sweep=True),
 }
 R = 600 * 800
 
@@ -411,6 +416,116 @@ def run_integration(args, wl, rank, local_rank, world):
         emit(out)
 
 
+def run_sweep(args, wl, rank, local_rank, world):
+    """cfg 4: a step = one 2^26-sample power buffer per GPU: FFT autocorrelation (device resident) and the score of every
+    refresh-rate hypothesis of allVideoConfigurations (first maximum of Gamma in each hypothesis' window).  Buffers are
+    independent: no collective on the data path (weak scaling); the 13 (rate, score, lag) triples per buffer stay on the
+    host of their rank."""
+    import torch
+    import torch.distributed as dist
+    import tempestsdr_b200 as tsdr
+    synth = _load(os.path.join(ROOT, "tempestsdr.jl_b200", "synth.py"), "_tsdr_synth")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, peak_src = peaks()
+    Fs, n = wl["Fs"], wl["n_ech"]
+    L = n // 2
+    ring = []
+    for i in range(wl["ring"]):   # abs2.(IQ) as extract_configuration feeds it (src/GUI.jl:70)
+        z = synth.make_iq_torch(n, Fs, wl["x_t"], wl["y_t"], wl["fv"], dev, seed=700 + 10 * rank + i, t0=i * n)
+        ring.append((z[:, 0] * z[:, 0] + z[:, 1] * z[:, 1]).contiguous())
+        del z
+    torch.cuda.empty_cache()
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    st = work_stream.cuda_stream
+    plan = tsdr.AutocorrPlan(n, device=local_rank, stream=st)
+    gamma = torch.empty(L, device=dev, dtype=torch.float32)
+    rates = sorted(tsdr.get_refresh_rates(tsdr.allVideoConfigurations))
+
+    def step(x_ptr):
+        plan.exec(x_ptr, 1, L, gamma.data_ptr())
+        return tsdr.sweep_refresh_hypotheses(gamma.data_ptr(), L, Fs, rates, stream=st)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for i in range(args.warmup):
+        res = step(ring[i % len(ring)].data_ptr())
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = plan.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        res = step(ring[i % len(ring)].data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = plan.launch_count() - l0 + 2 * len(res) * args.steps   # findmax = partial + final kernel per hypothesis
+    t_end = time.perf_counter() + 0.3
+    while time.perf_counter() < t_end:
+        step(ring[0].data_ptr())
+    clocks = sampler.stop()
+    barrier()
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    per_2_24 = elapsed_ms / (world * args.steps * (n >> 24))      # whole job: ms per 2^24 samples
+    # autocorrelation kernels alone, for the roofline
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        plan.exec(ring[i % len(ring)].data_ptr(), 1, L, gamma.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    fft_ms = e0.elapsed_time(e1) / args.steps
+    algo = 4.0 * n + 4.0 * L
+    best = max(res, key=lambda r: r[1])
+    # end to end: pinned host power buffer -> H2D -> autocorrelation -> sweep -> the triples on the host
+    host = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+    for i, h in enumerate(host):
+        h.copy_(ring[i % len(ring)])
+    xdev = [torch.empty(n, device=dev, dtype=torch.float32) for _ in range(2)]
+    k = max(2, min(args.steps, 6))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(k):
+        xdev[i % 2].copy_(host[i % 2], non_blocking=True)
+        step(xdev[i % 2].data_ptr())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    out = {"metric": "autocorr ms per 2^24 samples (whole job, incl. the refresh-hypothesis sweep)", "value": per_2_24, "unit": "ms",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+           "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl["name"], "samples_per_step_per_gpu": n, "lags": L, "hypotheses": len(rates),
+                      "l2_policy": "ring of %d distinct %.0f MB device buffers (> 126 MB L2), no flush" % (len(ring), n * 4 / 1e6),
+                      "parallelism": "one buffer per GPU per step, no collective" if world > 1 else "single GPU",
+                      "detected": {"rate_hypothesis": best[0], "fv_hat": best[2], "lag_index": best[3]}},
+           "clocks": clocks,
+           "e2e": {"value": float(te.item()) * 1e3 / (world * k * (n >> 24)), "unit": "ms", "h2d_bytes_per_step": n * 4,
+                   "d2h_bytes_per_step": len(rates) * 12, "steps": k},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "kernel": "k3_p1..p5 (three-level autocorrelation, 5 launches)", "achieved": algo / (fft_ms * 1e-3) / 1e9,
+                        "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": algo / (fft_ms * 1e-3) / 1e9 / hbm_peak,
+                        "traffic": None, "algorithmic_bytes_per_launch": algo, "kernel_ms_per_launch": fft_ms}}
+    plan.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        emit(out)
+
+
 _REAL_STDOUT = None
 
 
@@ -454,6 +569,9 @@ def main():
         return
     if "total_frames" in wl:
         run_integration(args, wl, rank, local_rank, world)
+        return
+    if wl.get("sweep"):
+        run_sweep(args, wl, rank, local_rank, world)
         return
 
     import numpy as np

@@ -21,7 +21,7 @@ __all__ = [
     "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
     "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
     "Chain", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "TempestError", "RENDERING_SIZE",
-    "device_count",
+    "device_count", "set_device",
 ]
 
 RENDERING_SIZE = (600, 800)  # src/GUI.jl:10
@@ -29,6 +29,11 @@ RENDERING_SIZE = (600, 800)  # src/GUI.jl:10
 
 def device_count():
     return _lib.device_count()
+
+
+def set_device(device):
+    """device used by this thread's per-function (host-pointer) calls; handles (Chain, AutocorrPlan) carry their own"""
+    check(_lib.load().tsdr_set_device(int(device)))
 
 
 def _ptr(a):

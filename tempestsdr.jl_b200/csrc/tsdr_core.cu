@@ -392,6 +392,11 @@ int tsdr_findmax_f32(const float* v, size_t n, float* value, size_t* index1) {
 int tsdr_findmax_dev_f32(const float* v_dev, size_t n, float* value, size_t* index1, void* stream) {
     TSDR_REQUIRE(v_dev && n > 0, "findmax of an empty collection");
     TSDR_REQUIRE(n < 0xffffffffull, "vector too long");
+    // the vector (and the caller's stream) live on some device: work there, whatever tsdr_set_device last said
+    struct DeviceGuard { int saved; ~DeviceGuard() { g_device = saved; } } guard{g_device};
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, v_dev) == cudaSuccess && at.type == cudaMemoryTypeDevice) g_device = at.device;
+    else cudaGetLastError();
     int rc = ensure_device(); if (rc) return rc;
     void* d_part;
     const int parts = 512;

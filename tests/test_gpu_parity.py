@@ -521,6 +521,27 @@ def test_gpu_matches_committed_goldens():
     assert np.max(np.abs(got - G["autocorr_db"])) <= 1e-2
 
 
+def test_per_function_calls_on_second_gpu():
+    import torch
+    if tsdr.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(3)
+    v = rng.random(200001).astype(np.float32)
+    v[[777, 150000]] = 2.0                                   # first maximum wins
+    with torch.cuda.device(1):
+        x = torch.from_numpy(v).cuda()
+        s = torch.cuda.Stream()
+        val, idx = tsdr.findmax_device(x.data_ptr(), x.numel(), s.cuda_stream)   # device taken from the pointer
+    assert (float(val), idx) == (2.0, 778)
+    z = (rng.standard_normal(5001) + 1j * rng.standard_normal(5001)).astype(np.complex64)
+    try:
+        tsdr.set_device(1)
+        assert np.array_equal(tsdr.amDemod(z), orc.amDemod(z))
+    finally:
+        tsdr.set_device(0)
+    assert np.array_equal(tsdr.amDemod(z), orc.amDemod(z))
+
+
 def test_gpu_matches_committed_goldens_v2():
     # golden_v2.npz: Int16 ingest (bit-exact) and the GetSpectrum.jl functions (Float32 FFT tolerance)
     import hashlib
