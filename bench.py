@@ -467,7 +467,7 @@ def run_sweep(args, wl, rank, local_rank, world):
     e1.record()
     torch.cuda.synchronize()
     elapsed_ms = e0.elapsed_time(e1)
-    launches = plan.launch_count() - l0 + 2 * len(res) * args.steps   # findmax = partial + final kernel per hypothesis
+    launches = plan.launch_count() - l0 + 2 * args.steps   # + the two launches of the batched window search per step
     t_end = time.perf_counter() + 0.3
     while time.perf_counter() < t_end:
         step(ring[0].data_ptr())

@@ -93,6 +93,10 @@ int tsdr_autocorr_out_len(size_t len, double Fs, double min_delay, double max_de
 int tsdr_findmax_f32(const float* v, size_t n, float* value, size_t* index1);
 /* same on a DEVICE vector (windowed peak picks on a device-resident Gamma: pass v_dev + offset, window length);
  * stream: the cudaStream_t the vector was produced on (NULL = default stream) */
+/* the same for n_windows windows v_dev[lo0[w] .. lo0[w] + len[w]) of one device vector at once (0-based starts;
+ * index1[w] is 1-based inside window w): the refresh-hypothesis sweep of cfg 4 in two launches and one synchronise */
+int tsdr_findmax_windows_dev_f32(const float* v_dev, int n_windows, const size_t* lo0, const size_t* len, float* values,
+                                 size_t* index1, void* stream);
 int tsdr_findmax_dev_f32(const float* v_dev, size_t n, float* value, size_t* index1, void* stream);
 
 /* fullScale!(mat) = (mat .- min)/(max - min)     src/ScreenRenderer.jl:35-39 */

@@ -40,6 +40,8 @@ SIGNATURES = {
                                     C.POINTER(C.c_size_t)]),
     "tsdr_autocorr_out_len": (C.c_int, [C.c_size_t, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_size_t)]),
     "tsdr_findmax_f32": (C.c_int, [_vp, C.c_size_t, _fp, C.POINTER(C.c_size_t)]),
+    "tsdr_findmax_windows_dev_f32": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _fp,
+                                               C.POINTER(C.c_size_t), _vp]),
     "tsdr_findmax_dev_f32": (C.c_int, [_vp, C.c_size_t, _fp, C.POINTER(C.c_size_t), _vp]),
     "tsdr_full_scale_f32": (C.c_int, [_vp, _vp, C.c_size_t]),
     "tsdr_sync_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp)]),

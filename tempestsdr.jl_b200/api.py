@@ -17,7 +17,7 @@ from .video_configurations import (VideoMode, allVideoConfigurations, find_close
 
 __all__ = [
     "amDemod", "invert_amDemod", "fmDemod", "abs2", "sig_to_image", "downgradeImage", "naiveResampler", "init_resampler",
-    "calculate_autocorrelation", "zoom_autocorr", "getSpectrum", "getWelch", "getWaterfall", "findmax", "findmax_device", "sweep_refresh_hypotheses", "SyncXY", "vsync", "fullScale",
+    "calculate_autocorrelation", "zoom_autocorr", "getSpectrum", "getWelch", "getWaterfall", "findmax", "findmax_device", "findmax_windows_device", "sweep_refresh_hypotheses", "SyncXY", "vsync", "fullScale",
     "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
     "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
     "Chain", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "TempestError", "RENDERING_SIZE",
@@ -219,6 +219,17 @@ def findmax_device(ptr, n, stream=None):
     check(_lib.load().tsdr_findmax_dev_f32(C.c_void_p(ptr), int(n), C.byref(val), C.byref(idx),
                                            C.c_void_p(stream) if stream else None))
     return np.float32(val.value), idx.value
+
+
+def findmax_windows_device(ptr, starts0, lengths, stream=None):
+    """findmax of several windows of one device vector at once -> [(value, 1-based index inside the window)]"""
+    n = len(starts0)
+    lo = (C.c_size_t * n)(*[int(v) for v in starts0])
+    ln = (C.c_size_t * n)(*[int(v) for v in lengths])
+    vals = (C.c_float * n)()
+    idx = (C.c_size_t * n)()
+    check(_lib.load().tsdr_findmax_windows_dev_f32(C.c_void_p(ptr), n, lo, ln, vals, idx, C.c_void_p(stream) if stream else None))
+    return [(np.float32(vals[i]), int(idx[i])) for i in range(n)]
 
 
 def fullScale(mat):
@@ -571,7 +582,7 @@ def sweep_refresh_hypotheses(gamma_ptr, n_gamma, Fs, hypotheses=None, half_width
     needed on the data path; gather the small result lists on the host).  Returns [(rate, score_dB, fv_hat, lag_index)]."""
     if hypotheses is None:
         hypotheses = sorted(get_refresh_rates(allVideoConfigurations))
-    out = []
+    mine = []
     for i, r in enumerate(hypotheses):
         if i % world != rank:
             continue
@@ -579,7 +590,13 @@ def sweep_refresh_hypotheses(gamma_ptr, n_gamma, Fs, hypotheses=None, half_width
         hi = min(_round(1 / (r - half_width_hz) * Fs), n_gamma)
         if hi < lo or lo < 1:
             continue
-        val, idx = findmax_device(gamma_ptr + 4 * (lo - 1), hi - lo + 1, stream)
+        mine.append((r, lo, hi))
+    if not mine:
+        return []
+    # every window in one call: two launches and one synchronise instead of one of each per hypothesis
+    found = findmax_windows_device(gamma_ptr, [lo - 1 for _, lo, _ in mine], [hi - lo + 1 for _, lo, hi in mine], stream)
+    out = []
+    for (r, lo, _), (val, idx) in zip(mine, found):
         k = lo + idx - 1                      # 1-based index into Gamma; the reference reads it as lag k/Fs
         out.append((float(r), float(val), 1.0 / (k / Fs), int(k)))
     return out

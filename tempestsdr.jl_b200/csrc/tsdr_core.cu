@@ -238,6 +238,48 @@ __global__ void __launch_bounds__(kEwThreads) k_findmax_partial(const float* __r
     }
 }
 
+// findmax over up to kMaxWindows windows of one device vector in two launches: (parts, windows) blocks scan
+// their slices, then one warp per window folds the partial keys and fetches the winning element
+constexpr int kMaxWindows = 64;
+constexpr int kWindowParts = 16;
+struct Windows { unsigned int lo[kMaxWindows]; unsigned int len[kMaxWindows]; };
+__global__ void __launch_bounds__(kEwThreads) k_findmax_windows(const float* __restrict__ v, Windows w, unsigned long long* __restrict__ part) {
+    __shared__ unsigned long long sm[kEwThreads / 32];
+    const unsigned int lo = w.lo[blockIdx.y], len = w.len[blockIdx.y];
+    unsigned long long key = 0ull;
+    for (unsigned int i = blockIdx.x * kEwThreads + threadIdx.x; i < len; i += gridDim.x * kEwThreads) {
+        float x = v[(size_t)lo + i];
+        if (x == 0.0f) x = 0.0f;
+        const unsigned long long k = ((unsigned long long)ordered_bits(x) << 32) | (unsigned long long)(0xffffffffu - i);
+        key = k > key ? k : key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < kEwThreads / 32; ++q) key = sm[q] > key ? sm[q] : key;
+        part[blockIdx.y * kWindowParts + blockIdx.x] = key;
+    }
+}
+__global__ void __launch_bounds__(32) k_findmax_windows_final(const float* __restrict__ v, Windows w, const unsigned long long* __restrict__ part,
+                                                              float* __restrict__ values, unsigned int* __restrict__ index0) {
+    unsigned long long key = threadIdx.x < kWindowParts ? part[blockIdx.x * kWindowParts + threadIdx.x] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if (threadIdx.x == 0) {
+        const unsigned int i = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
+        index0[blockIdx.x] = i;
+        values[blockIdx.x] = v[(size_t)w.lo[blockIdx.x] + i];
+    }
+}
+
 }  // namespace tsdr
 
 using namespace tsdr;
@@ -385,6 +427,43 @@ int tsdr_findmax_f32(const float* v, size_t n, float* value, size_t* index1) {
     const size_t idx = (size_t)(0xffffffffu - (unsigned int)(best & 0xffffffffull));
     if (value) *value = v[idx];
     if (index1) *index1 = idx + 1;
+    return TSDR_OK;
+}
+
+/* findmax of n_windows windows v_dev[lo0[w] .. lo0[w]+len[w]) at once: two launches, one copy, one synchronise */
+int tsdr_findmax_windows_dev_f32(const float* v_dev, int n_windows, const size_t* lo0, const size_t* len, float* values,
+                                 size_t* index1, void* stream) {
+    TSDR_REQUIRE(v_dev && lo0 && len && values && index1 && n_windows >= 1, "NULL argument or no window");
+    struct DeviceGuard { int saved; ~DeviceGuard() { g_device = saved; } } guard{g_device};
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, v_dev) == cudaSuccess && at.type == cudaMemoryTypeDevice) g_device = at.device;
+    else cudaGetLastError();
+    int rc = ensure_device(); if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    void* d_scr;
+    if ((rc = scratch(2, (size_t)kMaxWindows * (kWindowParts * 8 + 8) + 16, &d_scr))) return rc;
+    unsigned long long* d_part = (unsigned long long*)d_scr;
+    float* d_val = (float*)(d_part + (size_t)kMaxWindows * kWindowParts);
+    unsigned int* d_idx = (unsigned int*)(d_val + kMaxWindows);
+    for (int w0 = 0; w0 < n_windows; w0 += kMaxWindows) {
+        const int nw = std::min(kMaxWindows, n_windows - w0);
+        Windows w;
+        memset(&w, 0, sizeof(w));
+        for (int i = 0; i < nw; ++i) {
+            TSDR_REQUIRE(len[w0 + i] > 0, "findmax of an empty collection (window %d)", w0 + i);
+            TSDR_REQUIRE(lo0[w0 + i] < 0xffffffffull && len[w0 + i] < 0xffffffffull, "window %d out of range", w0 + i);
+            w.lo[i] = (unsigned int)lo0[w0 + i]; w.len[i] = (unsigned int)len[w0 + i];
+        }
+        k_findmax_windows<<<dim3(kWindowParts, nw), kEwThreads, 0, st>>>(v_dev, w, d_part);
+        k_findmax_windows_final<<<nw, 32, 0, st>>>(v_dev, w, d_part, d_val, d_idx);
+        TSDR_CUDA(cudaGetLastError());
+        float hv[kMaxWindows];
+        unsigned int hi[kMaxWindows];
+        TSDR_CUDA(cudaMemcpyAsync(hv, d_val, nw * sizeof(float), cudaMemcpyDeviceToHost, st));
+        TSDR_CUDA(cudaMemcpyAsync(hi, d_idx, nw * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        TSDR_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < nw; ++i) { values[w0 + i] = hv[i]; index1[w0 + i] = (size_t)hi[i] + 1; }
+    }
     return TSDR_OK;
 }
 

@@ -604,6 +604,18 @@ def test_findmax_device_and_hypothesis_sweep(synth):
     halves = tsdr.sweep_refresh_hypotheses(out.data_ptr(), L, Fs, stream=s.cuda_stream, rank=0, world=2) + \
         tsdr.sweep_refresh_hypotheses(out.data_ptr(), L, Fs, stream=s.cuda_stream, rank=1, world=2)
     assert sorted(halves) == sorted(res)
+    # the batched window search against one findmax per window: negative values, ties (first wins), 70 windows (> one batch)
+    rng = np.random.default_rng(9)
+    v = rng.standard_normal(300000).astype(np.float32) - 3.0
+    v[1000:1010] = 5.0
+    vt = torch.from_numpy(v).cuda()
+    starts = [int(a) for a in rng.integers(0, 250000, 70)] + [995]
+    lens = [int(a) for a in rng.integers(1, 50000, 70)] + [30]
+    got = tsdr.findmax_windows_device(vt.data_ptr(), starts, lens, s.cuda_stream)
+    for (val, idx), a, n_w in zip(got, starts, lens):
+        rv, ri = orc.findmax(v[a:a + n_w])
+        assert (val, idx) == (rv, ri)
+    assert got[-1] == (np.float32(5.0), 6)
     plan.close()
 
 
