@@ -1022,8 +1022,10 @@ int tsdr_chain_reset(tsdr_chain* c) {
     { int rc = chain_join(c); if (rc) return rc; }
     TSDR_CUDA(cudaMemsetAsync(c->d_acc, 0, (size_t)kRenderN * 4, c->stream));
     TSDR_CUDA(cudaMemsetAsync(c->d_best, 0, (size_t)(c->max_frames + 1) * 2 * 8, c->stream));
-    TSDR_CUDA(cudaMemcpyAsync(c->d_best + 1, &kBestInit, 8, cudaMemcpyHostToDevice, c->stream));
-    TSDR_CUDA(cudaStreamSynchronize(c->stream));
+    // slot [0][1] = kBestInit (beta = 0 at centre 1): low word 0xffffffff, high word 0 -- set on the device so that
+    // reset stays asynchronous (a sharded integration resets once per block and must not drain the stream)
+    static_assert(kBestInit == 0x00000000ffffffffull, "the memset below writes exactly this pattern");
+    TSDR_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(c->d_best + 1), 0xff, 4, c->stream));
     c->last_frames = 0;
     return TSDR_OK;
 }
