@@ -92,12 +92,13 @@ int tsdr_autocorr_out_len(size_t len, double Fs, double min_delay, double max_de
  * Used for the refresh/line peak picks  src/GUI.jl:79, production/investigate_data.jl:60,80 */
 int tsdr_findmax_f32(const float* v, size_t n, float* value, size_t* index1);
 /* same on a DEVICE vector (windowed peak picks on a device-resident Gamma: pass v_dev + offset, window length);
- * stream: the cudaStream_t the vector was produced on (NULL = default stream) */
+ * stream: the cudaStream_t the vector was produced on (NULL = default stream).  The call runs on the device that
+ * owns v_dev, whatever tsdr_set_device last selected. */
+int tsdr_findmax_dev_f32(const float* v_dev, size_t n, float* value, size_t* index1, void* stream);
 /* the same for n_windows windows v_dev[lo0[w] .. lo0[w] + len[w]) of one device vector at once (0-based starts;
  * index1[w] is 1-based inside window w): the refresh-hypothesis sweep of cfg 4 in two launches and one synchronise */
 int tsdr_findmax_windows_dev_f32(const float* v_dev, int n_windows, const size_t* lo0, const size_t* len, float* values,
                                  size_t* index1, void* stream);
-int tsdr_findmax_dev_f32(const float* v_dev, size_t n, float* value, size_t* index1, void* stream);
 
 /* fullScale!(mat) = (mat .- min)/(max - min)     src/ScreenRenderer.jl:35-39 */
 int tsdr_full_scale_f32(const float* in, float* out, size_t n);
