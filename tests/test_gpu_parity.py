@@ -521,6 +521,48 @@ def test_gpu_matches_committed_goldens():
     assert np.max(np.abs(got - G["autocorr_db"])) <= 1e-2
 
 
+def test_two_host_threads_call_concurrently(synth):
+    # coreProcessing runs on a worker thread (src/GUI.jl:381) while extract_configuration runs on the GUI thread
+    # (:411-419): per-function calls, a chain and an autocorrelation from two threads at once must not interfere
+    import threading
+    Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)
+    S = orc.frame_samples(Fs, fv)
+    iq = synth.make_iq(2 * S, Fs, x_t, y_t, fv, seed=91)
+    power = orc.abs2(iq[: 1 << 15])
+    want_env = orc.amDemod(iq)
+    want_g, _ = orc.calculate_autocorrelation(power, float(1 << 15), 0, 0.5)
+    so = orc.SyncXY()
+    want_img, _, want_sy, want_sx = orc.chain_buffer(iq, Fs, x_t, y_t, fv, 0.3, so, np.zeros((600, 800), np.float32), publish=False)
+    errors = []
+
+    def worker():      # the processing thread: chain + demodulation
+        try:
+            for _ in range(6):
+                ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=0.3, max_samples=iq.size)
+                ch.push(iq)
+                sy, sx = ch.offsets()
+                assert np.array_equal(ch.image(), want_img) and np.array_equal(sy, want_sy) and np.array_equal(sx, want_sx)
+                ch.close()
+                assert np.array_equal(tsdr.amDemod(iq), want_env)
+        except Exception as exc:  # noqa: BLE001
+            errors.append(("worker", repr(exc)))
+
+    def gui():         # the GUI thread: configuration estimate
+        try:
+            for _ in range(12):
+                g, _ = tsdr.calculate_autocorrelation(power, float(1 << 15), 0, 0.5)
+                assert np.max(np.abs(g - want_g)) <= 1e-2
+                v, i = tsdr.findmax(g)
+                assert (v, i) == tsdr.findmax(g)
+        except Exception as exc:  # noqa: BLE001
+            errors.append(("gui", repr(exc)))
+
+    ts = [threading.Thread(target=worker), threading.Thread(target=gui)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+
+
 def test_per_function_calls_on_second_gpu():
     import torch
     if tsdr.device_count() < 2:
