@@ -51,10 +51,12 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p1(FftParams p) {
     extern __shared__ __align__(16) float2 sm[];
     constexpr int LOGC = F::LOGC1_v, C = 1 << LOGC, HALF = C / 2, NA = F::NA_v;
     __shared__ float2 tw_s[NA];
+    __shared__ float2 tw_step[NA];   // W_M^ka: the twiddle of column r + 1 is the twiddle of column r times this
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x << LOGC;
     const ColLayoutCt<LOGC> lay;
     load_twiddles<F::LOGNA_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
+    for (int k = tid; k < NA; k += F::NT_v) tw_step[k] = twiddle_n(p, 2 * (int64_t)k);
 #pragma unroll
     for (int e = tid; e < NA * HALF; e += F::NT_v) {
         const int a = e / HALF, c2 = (e - a * HALF) * 2;
@@ -71,14 +73,18 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p1(FftParams p) {
     }
     __syncthreads();
     fft_fwd_ct<F::LOGNA_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGNA_v, F::NT_v>(sm, lay, tw_s, tid);
+    // two adjacent columns per thread: one table look-up W_M^(ka r); the neighbour's twiddle is that times the
+    // row's step W_M^ka from shared memory (the second look-up per pair was the main stall of this loop;
+    // four columns per look-up brought nothing more)
 #pragma unroll 4
     for (int e = tid; e < NA * HALF; e += F::NT_v) {
         const int rho = e / HALF, c2 = (e - rho * HALF) * 2;
         const int ka = digit_rev_ct<F::LOGNA_v>(rho);
         const int r = r0 + c2;
         const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, rho)]);
-        const float2 a = cmul(make_float2(sv.x, sv.y), twiddle_n(p, 2 * (int64_t)ka * r));        // W_M^(ka r) = W_N^(2 ka r)
-        const float2 b = cmul(make_float2(sv.z, sv.w), twiddle_n(p, 2 * (int64_t)ka * (r + 1)));
+        const float2 wa = twiddle_n(p, 2 * (int64_t)ka * r);                                      // W_M^(ka r) = W_N^(2 ka r)
+        const float2 a = cmul(make_float2(sv.x, sv.y), wa);
+        const float2 b = cmul(make_float2(sv.z, sv.w), cmul(wa, tw_step[ka]));
         reinterpret_cast<float4*>(p.T)[(((int64_t)ka << F::LOGNBC_v) + r) >> 1] = make_float4(a.x, a.y, b.x, b.y);
     }
 }
@@ -95,7 +101,10 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
     const ColLayoutCt<LOGC> lay;
     float4* T4 = reinterpret_cast<float4*>(p.T);
     __shared__ float2 tw_s[NB];
+    __shared__ float2 tw_step[NB];   // forward: W_M'^kb, the step from column c to c + 1
     load_twiddles<F::LOGNB_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
+    if (DIR > 0) for (int k = tid; k < NB; k += F::NT_v) tw_step[k] = twiddle_n(p, (int64_t)k << (F::LOGNA_v + 1));
+    const float2 step_inv = cconj(twiddle_n(p, 2 * (int64_t)ka));   // inverse: conj W_M^ka, the same for the whole CTA
 #pragma unroll
     for (int e = tid; e < NB * HALF; e += F::NT_v) {
         const int i = e / HALF, c2 = (e - i * HALF) * 2;   // forward: i = b ; inverse: i = kb
@@ -114,13 +123,15 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
         int i;
         if (DIR > 0) {   // position pos holds kb; stage-2 twiddle W_M'^(kb c) = W_N^(2 NA kb c)
             i = digit_rev_ct<F::LOGNB_v>(pos);
-            a = cmul(make_float2(sv.x, sv.y), twiddle_n(p, ((int64_t)i * c) << (F::LOGNA_v + 1)));
-            b = cmul(make_float2(sv.z, sv.w), twiddle_n(p, ((int64_t)i * (c + 1)) << (F::LOGNA_v + 1)));
+            const float2 wa = twiddle_n(p, ((int64_t)i * c) << (F::LOGNA_v + 1));
+            a = cmul(make_float2(sv.x, sv.y), wa);
+            b = cmul(make_float2(sv.z, sv.w), cmul(wa, tw_step[i]));
         } else {         // position pos holds b; undo the stage-1 twiddle W_M^(ka r), r = b NC + c
             i = pos;
             const int64_t r = ((int64_t)i << F::LOGNC_v) + c;
-            a = cmul(make_float2(sv.x, sv.y), cconj(twiddle_n(p, 2 * (int64_t)ka * r)));
-            b = cmul(make_float2(sv.z, sv.w), cconj(twiddle_n(p, 2 * (int64_t)ka * (r + 1))));
+            const float2 wa = cconj(twiddle_n(p, 2 * (int64_t)ka * r));
+            a = cmul(make_float2(sv.x, sv.y), wa);
+            b = cmul(make_float2(sv.z, sv.w), cmul(wa, step_inv));
         }
         T4[(base + ((int64_t)i << F::LOGNC_v) + c2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
     }
@@ -137,11 +148,23 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
     const RowLayoutCt lay{F::kRowStride_v};
     float4* T4 = reinterpret_cast<float4*>(p.T);
     __shared__ float2 tw_s[NC];
+    __shared__ float2 tw_c[NC];        // W_N^(kc NA NB): with tw_row, the unpack twiddle W_N^k of k = ka + NA kb + NA NB kc
+    __shared__ float2 tw_row[R];       // W_N^(ka + NA kb) of slot s (row A)
+    __shared__ float2 tw_rstep[2 * R]; // conj W_M'^kb of smem row srow: the step from column c to c + 1 in the write-back
     load_twiddles<LOGNC, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
     // slot s in [0, R): rows (rowA, rowB); smem row s holds rowA, smem row R + s holds rowB
     auto rowA_of = [&](int s) { return special ? t0 + s : NB + t0 + s; };
     auto rowB_of = [&](int s) { return special ? ((NB - (t0 + s)) & (NB - 1)) : NA * NB - 1 - (t0 + s); };
     auto valid = [&](int s) { return !special || t0 + s <= NB / 2; };
+    for (int k = tid; k < NC; k += F::NT_v) tw_c[k] = twiddle_n(p, (int64_t)k << (LOGNA + LOGNB));
+    if (tid < R) {
+        const int rowA = rowA_of(tid);
+        tw_row[tid] = twiddle_n(p, (int64_t)(rowA >> LOGNB) + ((int64_t)(rowA & (NB - 1)) << LOGNA));
+    }
+    if (tid < 2 * R) {
+        const int row = tid < R ? rowA_of(tid) : rowB_of(tid - R);
+        tw_rstep[tid] = cconj(twiddle_n(p, (int64_t)(row & (NB - 1)) << (LOGNA + 1)));
+    }
 #pragma unroll
     for (int e = tid; e < 2 * R * (NC / 2); e += F::NT_v) {
         const int srow = e / (NC / 2), i2 = (e - srow * (NC / 2)) * 2;
@@ -161,11 +184,10 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
         const int s = e >> LOGNC, kc = e & (NC - 1);
         if (!valid(s)) continue;
         const int rowA = rowA_of(s), rowB = rowB_of(s);
-        const int ka = rowA >> LOGNB, kb = rowA & (NB - 1);
-        const int64_t k = (int64_t)ka + ((int64_t)kb << LOGNA) + ((int64_t)kc << (LOGNA + LOGNB));
+        const float2 w = cmul(tw_row[s], tw_c[kc]);   // W_N^k, k = ka + NA kb + NA NB kc
         const int posk = digit_pos_ct<LOGNC>(kc);
         if (rowA != rowB) {
-            mid_pair(p, sm[lay(s, posk)], sm[lay(R + s, digit_pos_ct<LOGNC>(NC - 1 - kc))], k, sc);
+            mid_pair_w(sm[lay(s, posk)], sm[lay(R + s, digit_pos_ct<LOGNC>(NC - 1 - kc))], w, sc);
         } else if (rowA == 0) {       // (0,0,kc) <-> (0,0,(NC-kc) mod NC)
             if (kc > NC / 2) continue;
             if (kc == 0) {
@@ -175,13 +197,13 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
             } else {
                 const int pos2 = digit_pos_ct<LOGNC>(NC - kc);
                 float2 a = sm[lay(s, posk)], b = sm[lay(s, pos2)];
-                mid_pair(p, a, b, k, sc);
+                mid_pair_w(a, b, w, sc);
                 sm[lay(s, posk)] = a;
                 if (pos2 != posk) sm[lay(s, pos2)] = b;
             }
         } else {                      // row (0, NB/2): kc <-> NC-1-kc inside the row
             if (kc >= NC / 2) continue;
-            mid_pair(p, sm[lay(s, posk)], sm[lay(s, digit_pos_ct<LOGNC>(NC - 1 - kc))], k, sc);
+            mid_pair_w(sm[lay(s, posk)], sm[lay(s, digit_pos_ct<LOGNC>(NC - 1 - kc))], w, sc);
         }
     }
     __syncthreads();
@@ -195,8 +217,9 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
         if (srow >= R && rowA == rowB) continue;
         const int row = srow < R ? rowA : rowB;
         const int kb = row & (NB - 1);
-        const float2 a = cmul(sm[lay(srow, c2)], cconj(twiddle_n(p, ((int64_t)kb * c2) << (LOGNA + 1))));
-        const float2 b = cmul(sm[lay(srow, c2 + 1)], cconj(twiddle_n(p, ((int64_t)kb * (c2 + 1)) << (LOGNA + 1))));
+        const float2 wa = cconj(twiddle_n(p, ((int64_t)kb * c2) << (LOGNA + 1)));
+        const float2 a = cmul(sm[lay(srow, c2)], wa);
+        const float2 b = cmul(sm[lay(srow, c2 + 1)], cmul(wa, tw_rstep[srow]));
         T4[(((int64_t)row << LOGNC) + c2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
     }
 }

@@ -162,17 +162,20 @@ __global__ void __launch_bounds__(kFastThreads, 3) k_fft_cols_ct(FftParams p) {
 }
 
 // ------------------------------------------------------------------------- middle --
-__device__ __forceinline__ void mid_pair(const FftParams& p, float2& zk_io, float2& zm_io, int64_t k, float sc) {
+// w = W_N^k
+__device__ __forceinline__ void mid_pair_w(float2& zk_io, float2& zm_io, const float2 w, float sc) {
     const float2 zk = zk_io, zm = zm_io;
     const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
     const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-    const float2 w = twiddle_n(p, k);
     const float2 wO = cmul(w, O);
     const float2 xp = cadd(E, wO), xm = csub(E, wO);
     const float P = fmaf(xp.x, xp.x, xp.y * xp.y), Pm = fmaf(xm.x, xm.x, xm.y * xm.y);
     const float S = (P + Pm) * sc, D = (P - Pm) * sc;
     zk_io = make_float2(S + w.y * D, w.x * D);   // Y[k]   = S + i conj(w) D
     zm_io = make_float2(S - w.y * D, w.x * D);   // Y[M-k] = S + i w D
+}
+__device__ __forceinline__ void mid_pair(const FftParams& p, float2& zk_io, float2& zm_io, int64_t k, float sc) {
+    mid_pair_w(zk_io, zm_io, twiddle_n(p, k), sc);
 }
 
 template <int LOGA, int LOGB, int LOGNB>
