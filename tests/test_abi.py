@@ -72,3 +72,52 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import orc" not in txt and "oracle_np" not in txt and "tsdr_oracle" not in txt, f
+
+
+def test_julia_wrapper_binds_declared_symbols_with_matching_arity():
+    """The Julia ccall wrapper cannot be executed here (no Julia in the image): check statically that every
+    symbol it binds is declared in include/tempest_b200.h and that each ccall passes as many argument types
+    as the C prototype has parameters."""
+    import re
+    from tempestsdr_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "tempestsdr.jl_b200", "julia", "TempestSDRB200.jl"), encoding="utf-8").read()
+    calls = list(re.finditer(r"\(:(tsdr_[a-z0-9_]+), LIB\),\s*([A-Za-z]+),\s*\(", src))
+    assert len(calls) >= 25
+    seen = set()
+    for m in calls:
+        name = m.group(1)
+        assert name in _lib.SIGNATURES, "Julia wrapper binds %s, which the header does not declare" % name
+        i, depth = m.end(), 1            # scan the argument-type tuple to its closing parenthesis
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        tup = src[m.end():i - 1]
+        # top-level commas only (Ptr{Ptr{Cvoid}} has none, but stay safe with braces)
+        parts, level, cur = [], 0, ""
+        for ch in tup:
+            if ch in "{(":
+                level += 1
+            elif ch in "})":
+                level -= 1
+            if ch == "," and level == 0:
+                parts.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            parts.append(cur)
+        n_julia = len([p for p in parts if p.strip()])
+        n_c = len(_lib.SIGNATURES[name][1])
+        assert n_julia == n_c, "%s: Julia passes %d argument types, the C prototype has %d" % (name, n_julia, n_c)
+        ret = m.group(2)
+        want = {"c_int": "Cint", "c_char_p": "Cstring", "c_ulong": "Csize_t", "c_size_t": "Csize_t"}.get(
+            _lib.SIGNATURES[name][0].__name__, None)
+        assert want is None or ret == want, "%s: return type %s vs %s" % (name, ret, want)
+        seen.add(name)
+    # the functions INTEGRATION.md promises are all bound
+    for must in ("tsdr_am_demod_f32", "tsdr_sig_to_image_f32", "tsdr_downgrade_f32", "tsdr_autocorr_f32", "tsdr_vsync_f32",
+                 "tsdr_chain_create", "tsdr_chain_push_host", "tsdr_chain_push_host_i16", "tsdr_chain_push_ring",
+                 "tsdr_ring_create", "tsdr_ring_put", "tsdr_ring_take", "tsdr_get_spectrum_f32", "tsdr_get_welch_f32",
+                 "tsdr_get_waterfall_f32", "tsdr_upsampler_create"):
+        assert must in seen, must
