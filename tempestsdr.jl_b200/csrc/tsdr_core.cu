@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kEwThreads) k_demod(const float2* __restrict__
     if (i + 1 < n) {
         const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(iq) + pair);
         float2 o;
-        if (MODE == 0) { o.x = dev_hypotf(v.x, v.y); o.y = dev_hypotf(v.z, v.w); }
+        if (MODE == 0) dev_hypotf2(v.x, v.y, v.z, v.w, o.x, o.y);
         else { o.x = __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)); o.y = __fadd_rn(__fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w)); }
         reinterpret_cast<float2*>(out)[pair] = o;
     } else if (i < n) {
