@@ -920,7 +920,11 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     ap.published = (c->flags & TSDR_CHAIN_PUBLISH_ALL) ? c->d_published : nullptr;
     ap.n_frames = nb; ap.alpha = c->alpha; ap.one_minus_alpha = 1.0f - c->alpha;
     ap.align = align; ap.sum_mode = (c->flags & TSDR_CHAIN_SUM) ? 1 : 0;
-    if (!prime) { k_accumulate<<<kRenderH, kAccThreads, 0, st2>>>(ap); c->launches += 1; }
+    if (!prime) {
+        if (ap.align && !ap.sum_mode && !ap.published) k_accumulate<true><<<kRenderH, kAccThreads, 0, st2>>>(ap);
+        else k_accumulate<false><<<kRenderH, kAccThreads, 0, st2>>>(ap);
+        c->launches += 1;
+    }
     if (align) { k_sync_carry<<<1, 256, 0, st2>>>(c->d_best, nb, c->d_sy, c->d_sx); c->launches += 1; }
     mark(st2);
     if (host_image) {
