@@ -102,8 +102,14 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
     float4* T4 = reinterpret_cast<float4*>(p.T);
     __shared__ float2 tw_s[NB];
     __shared__ float2 tw_step[NB];   // forward: W_M'^kb, the step from column c to c + 1
+                                     // inverse: conj W_M^(ka b NC), the row part of conj W_M^(ka r), r = b NC + c
+    __shared__ float2 tw_col[HALF];  // inverse: conj W_M^(ka (c0 + 2 j)), its column part
     load_twiddles<F::LOGNB_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
     if (DIR > 0) for (int k = tid; k < NB; k += F::NT_v) tw_step[k] = twiddle_n(p, (int64_t)k << (F::LOGNA_v + 1));
+    else {
+        for (int k = tid; k < NB; k += F::NT_v) tw_step[k] = cconj(twiddle_n(p, (2 * (int64_t)ka * k) << F::LOGNC_v));
+        if (tid < HALF) tw_col[tid] = cconj(twiddle_n(p, 2 * (int64_t)ka * (c0 + 2 * tid)));
+    }
     const float2 step_inv = cconj(twiddle_n(p, 2 * (int64_t)ka));   // inverse: conj W_M^ka, the same for the whole CTA
 #pragma unroll
     for (int e = tid; e < NB * HALF; e += F::NT_v) {
@@ -128,8 +134,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
             b = cmul(make_float2(sv.z, sv.w), cmul(wa, tw_step[i]));
         } else {         // position pos holds b; undo the stage-1 twiddle W_M^(ka r), r = b NC + c
             i = pos;
-            const int64_t r = ((int64_t)i << F::LOGNC_v) + c;
-            const float2 wa = cconj(twiddle_n(p, 2 * (int64_t)ka * r));
+            const float2 wa = cmul(tw_step[i], tw_col[c2 >> 1]);
             a = cmul(make_float2(sv.x, sv.y), wa);
             b = cmul(make_float2(sv.z, sv.w), cmul(wa, step_inv));
         }
@@ -151,6 +156,8 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
     __shared__ float2 tw_c[NC];        // W_N^(kc NA NB): with tw_row, the unpack twiddle W_N^k of k = ka + NA kb + NA NB kc
     __shared__ float2 tw_row[R];       // W_N^(ka + NA kb) of slot s (row A)
     __shared__ float2 tw_rstep[2 * R]; // conj W_M'^kb of smem row srow: the step from column c to c + 1 in the write-back
+    __shared__ float2 tw_hi[2 * R][NC / 16];   // conj W_M'^(kb 16 ch) and
+    __shared__ float2 tw_lo[2 * R][8];         // conj W_M'^(kb cl), cl even: the write-back twiddle of column 16 ch + cl
     load_twiddles<LOGNC, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
     // slot s in [0, R): rows (rowA, rowB); smem row s holds rowA, smem row R + s holds rowB
     auto rowA_of = [&](int s) { return special ? t0 + s : NB + t0 + s; };
@@ -164,6 +171,13 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
     if (tid < 2 * R) {
         const int row = tid < R ? rowA_of(tid) : rowB_of(tid - R);
         tw_rstep[tid] = cconj(twiddle_n(p, (int64_t)(row & (NB - 1)) << (LOGNA + 1)));
+    }
+    for (int e = tid; e < 2 * R * (NC / 16 + 8); e += F::NT_v) {
+        const int srow = e / (NC / 16 + 8), q = e - srow * (NC / 16 + 8);
+        const int row = srow < R ? rowA_of(srow) : rowB_of(srow - R);
+        const int64_t kb = row & (NB - 1);
+        if (q < NC / 16) tw_hi[srow][q] = cconj(twiddle_n(p, (kb * 16 * q) << (LOGNA + 1)));
+        else tw_lo[srow][q - NC / 16] = cconj(twiddle_n(p, (kb * 2 * (q - NC / 16)) << (LOGNA + 1)));
     }
 #pragma unroll
     for (int e = tid; e < 2 * R * (NC / 2); e += F::NT_v) {
@@ -216,8 +230,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
         const int rowA = rowA_of(s), rowB = rowB_of(s);
         if (srow >= R && rowA == rowB) continue;
         const int row = srow < R ? rowA : rowB;
-        const int kb = row & (NB - 1);
-        const float2 wa = cconj(twiddle_n(p, ((int64_t)kb * c2) << (LOGNA + 1)));
+        const float2 wa = cmul(tw_hi[srow][c2 >> 4], tw_lo[srow][(c2 & 15) >> 1]);
         const float2 a = cmul(sm[lay(srow, c2)], wa);
         const float2 b = cmul(sm[lay(srow, c2 + 1)], cmul(wa, tw_rstep[srow]));
         T4[(((int64_t)row << LOGNC) + c2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
