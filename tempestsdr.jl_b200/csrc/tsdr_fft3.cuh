@@ -57,6 +57,15 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p1(FftParams p) {
     const ColLayoutCt<LOGC> lay;
     load_twiddles<F::LOGNA_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
     for (int k = tid; k < NA; k += F::NT_v) tw_step[k] = twiddle_n(p, 2 * (int64_t)k);
+    // W_M^(ka r) for the CTA's columns r = r0 + 2 j as the product of two small tables over ka = 16 kh + kl
+    __shared__ float2 tw_kh[NA / 16][HALF];
+    __shared__ float2 tw_kl[16][HALF];
+    for (int e = tid; e < (NA / 16 + 16) * HALF; e += F::NT_v) {
+        const int q = e / HALF, jj = e - q * HALF;
+        const int64_t r = r0 + 2 * jj;
+        if (q < NA / 16) tw_kh[q][jj] = twiddle_n(p, 2 * (int64_t)(16 * q) * r);
+        else tw_kl[q - NA / 16][jj] = twiddle_n(p, 2 * (int64_t)(q - NA / 16) * r);
+    }
 #pragma unroll
     for (int e = tid; e < NA * HALF; e += F::NT_v) {
         const int a = e / HALF, c2 = (e - a * HALF) * 2;
@@ -82,7 +91,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p1(FftParams p) {
         const int ka = digit_rev_ct<F::LOGNA_v>(rho);
         const int r = r0 + c2;
         const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, rho)]);
-        const float2 wa = twiddle_n(p, 2 * (int64_t)ka * r);                                      // W_M^(ka r) = W_N^(2 ka r)
+        const float2 wa = cmul(tw_kh[ka >> 4][c2 >> 1], tw_kl[ka & 15][c2 >> 1]);                 // W_M^(ka r) = W_N^(2 ka r)
         const float2 a = cmul(make_float2(sv.x, sv.y), wa);
         const float2 b = cmul(make_float2(sv.z, sv.w), cmul(wa, tw_step[ka]));
         reinterpret_cast<float4*>(p.T)[(((int64_t)ka << F::LOGNBC_v) + r) >> 1] = make_float4(a.x, a.y, b.x, b.y);
@@ -105,8 +114,17 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
                                      // inverse: conj W_M^(ka b NC), the row part of conj W_M^(ka r), r = b NC + c
     __shared__ float2 tw_col[HALF];  // inverse: conj W_M^(ka (c0 + 2 j)), its column part
     load_twiddles<F::LOGNB_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
-    if (DIR > 0) for (int k = tid; k < NB; k += F::NT_v) tw_step[k] = twiddle_n(p, (int64_t)k << (F::LOGNA_v + 1));
-    else {
+    __shared__ float2 tw_kh[NB / 16][HALF];   // forward: W_M'^(kb c) for c = c0 + 2 j, kb = 16 kh + kl, as a product
+    __shared__ float2 tw_kl[16][HALF];
+    if (DIR > 0) {
+        for (int k = tid; k < NB; k += F::NT_v) tw_step[k] = twiddle_n(p, (int64_t)k << (F::LOGNA_v + 1));
+        for (int e = tid; e < (NB / 16 + 16) * HALF; e += F::NT_v) {
+            const int q = e / HALF, jj = e - q * HALF;
+            const int64_t c = c0 + 2 * jj;
+            if (q < NB / 16) tw_kh[q][jj] = twiddle_n(p, ((int64_t)(16 * q) * c) << (F::LOGNA_v + 1));
+            else tw_kl[q - NB / 16][jj] = twiddle_n(p, ((int64_t)(q - NB / 16) * c) << (F::LOGNA_v + 1));
+        }
+    } else {
         for (int k = tid; k < NB; k += F::NT_v) tw_step[k] = cconj(twiddle_n(p, (2 * (int64_t)ka * k) << F::LOGNC_v));
         if (tid < HALF) tw_col[tid] = cconj(twiddle_n(p, 2 * (int64_t)ka * (c0 + 2 * tid)));
     }
@@ -129,7 +147,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
         int i;
         if (DIR > 0) {   // position pos holds kb; stage-2 twiddle W_M'^(kb c) = W_N^(2 NA kb c)
             i = digit_rev_ct<F::LOGNB_v>(pos);
-            const float2 wa = twiddle_n(p, ((int64_t)i * c) << (F::LOGNA_v + 1));
+            const float2 wa = cmul(tw_kh[i >> 4][c2 >> 1], tw_kl[i & 15][c2 >> 1]);
             a = cmul(make_float2(sv.x, sv.y), wa);
             b = cmul(make_float2(sv.z, sv.w), cmul(wa, tw_step[i]));
         } else {         // position pos holds b; undo the stage-1 twiddle W_M^(ka r), r = b NC + c
