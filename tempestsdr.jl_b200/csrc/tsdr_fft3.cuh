@@ -12,6 +12,10 @@
 // Rows/columns are stored in NATURAL frequency order between passes (the digit reversal of the
 // in-place DIF/DIT butterflies stays inside shared memory), and P2..P4 work in place, so the
 // whole working set is one M-point buffer (64 MB at n = 2^24) that fits the 126 MB L2.
+// Twiddles: the long-transform factors W_N^t live in two global tables (lo/hi split); inside the kernels every
+// per-element twiddle is the product of two entries of small per-CTA shared-memory tables (index split such as
+// ka = 16 kh + kl, filled with a few hundred look-ups per CTA), and the second column of each pair is the first
+// times the row's step -- the global look-ups per element were the main stall of the first version.
 //
 // Frequency index: k = ka + NA (kb + NB kc).  Mirror M-k used by the real-input unpack:
 //   ka > 0          : (NA-ka, NB-1-kb, NC-1-kc)   -> row rho = ka NB + kb  pairs with  NA NB + NB - 1 - rho
