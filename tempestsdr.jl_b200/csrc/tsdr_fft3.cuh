@@ -201,6 +201,45 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
         if (q < NC / 16) tw_hi[srow][q] = cconj(twiddle_n(p, (kb * 16 * q) << (LOGNA + 1)));
         else tw_lo[srow][q - NC / 16] = cconj(twiddle_n(p, (kb * 2 * (q - NC / 16)) << (LOGNA + 1)));
     }
+    if (!special) {
+        // The regular CTAs (all but a handful): every slot is valid and row A never equals row B, and because the
+        // thread count is a multiple of the row length each thread keeps ONE column (pair) for the whole kernel --
+        // its digit-reversed positions and its column twiddle are computed once instead of per element.
+        static_assert(F::NT_v % NC == 0 && F::NT_v % (NC / 2) == 0, "threads per CTA must be a multiple of the row length");
+        constexpr int ROWS_PER_IT = F::NT_v / (NC / 2);          // rows covered by one pass of the load / store loops
+        const int c2 = (tid & (NC / 2 - 1)) * 2;
+        const int rsub = tid / (NC / 2);
+        const int rowA0 = NB + t0, rowB0 = NA * NB - 1 - t0;     // rowA_of(s) = rowA0 + s, rowB_of(s) = rowB0 - s
+#pragma unroll
+        for (int srow = rsub; srow < 2 * R; srow += ROWS_PER_IT) {
+            const int row = srow < R ? rowA0 + srow : rowB0 - (srow - R);
+            const float4 v = T4[(((int64_t)row << LOGNC) + c2) >> 1];
+            sm[lay(srow, c2)] = make_float2(v.x, v.y);
+            sm[lay(srow, c2 + 1)] = make_float2(v.z, v.w);
+        }
+        __syncthreads();
+        fft_fwd_ct<LOGNC, 0, false, F::LOGR_v + 1, RowLayoutCt, LOGNC, F::NT_v>(sm, lay, tw_s, tid);
+        {
+            const float sc = 0.5f * p.inv_scale;
+            const int kc = tid & (NC - 1);
+            const int posk = digit_pos_ct<LOGNC>(kc), posm = digit_pos_ct<LOGNC>(NC - 1 - kc);
+            const float2 wc = tw_c[kc];
+            for (int sl = tid >> LOGNC; sl < R; sl += F::NT_v >> LOGNC)
+                mid_pair_w(sm[lay(sl, posk)], sm[lay(R + sl, posm)], cmul(tw_row[sl], wc), sc);
+        }
+        __syncthreads();
+        fft_inv_ct<LOGNC, CtPlan<LOGNC>::nst - 1, false, F::LOGR_v + 1, RowLayoutCt, LOGNC, F::NT_v>(sm, lay, tw_s, tid);
+#pragma unroll
+        for (int srow = rsub; srow < 2 * R; srow += ROWS_PER_IT) {
+            const int row = srow < R ? rowA0 + srow : rowB0 - (srow - R);
+            const float2 wa = cmul(tw_hi[srow][c2 >> 4], tw_lo[srow][(c2 & 15) >> 1]);
+            const float2 a = cmul(sm[lay(srow, c2)], wa);
+            const float2 b = cmul(sm[lay(srow, c2 + 1)], cmul(wa, tw_rstep[srow]));
+            T4[(((int64_t)row << LOGNC) + c2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
+        }
+        return;
+    }
+    // ---- the special CTAs: rows with ka = 0, whose mirrors lie in the same row set
 #pragma unroll
     for (int e = tid; e < 2 * R * (NC / 2); e += F::NT_v) {
         const int srow = e / (NC / 2), i2 = (e - srow * (NC / 2)) * 2;
