@@ -70,9 +70,10 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p1(FftParams p) {
         if (q < NA / 16) tw_kh[q][jj] = twiddle_n(p, 2 * (int64_t)(16 * q) * r);
         else tw_kl[q - NA / 16][jj] = twiddle_n(p, 2 * (int64_t)(q - NA / 16) * r);
     }
+    static_assert(F::NT_v % HALF == 0, "each thread keeps one column pair");
+    const int c2 = (tid & (HALF - 1)) * 2;       // this thread's column pair in every loop below
 #pragma unroll
-    for (int e = tid; e < NA * HALF; e += F::NT_v) {
-        const int a = e / HALF, c2 = (e - a * HALF) * 2;
+    for (int a = tid / HALF; a < NA; a += F::NT_v / HALF) {
         const int64_t j = ((int64_t)a << F::LOGNBC_v) + r0 + c2;
         float4 v;
         if (!PADDED || 2 * j + 3 < p.n_valid) v = __ldg(reinterpret_cast<const float4*>(p.x) + (j >> 1));
@@ -89,11 +90,10 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p1(FftParams p) {
     // two adjacent columns per thread: one table look-up W_M^(ka r); the neighbour's twiddle is that times the
     // row's step W_M^ka from shared memory (the second look-up per pair was the main stall of this loop;
     // four columns per look-up brought nothing more)
+    const int r = r0 + c2;
 #pragma unroll 4
-    for (int e = tid; e < NA * HALF; e += F::NT_v) {
-        const int rho = e / HALF, c2 = (e - rho * HALF) * 2;
+    for (int rho = tid / HALF; rho < NA; rho += F::NT_v / HALF) {
         const int ka = digit_rev_ct<F::LOGNA_v>(rho);
-        const int r = r0 + c2;
         const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, rho)]);
         const float2 wa = cmul(tw_kh[ka >> 4][c2 >> 1], tw_kl[ka & 15][c2 >> 1]);                 // W_M^(ka r) = W_N^(2 ka r)
         const float2 a = cmul(make_float2(sv.x, sv.y), wa);
@@ -133,9 +133,10 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
         if (tid < HALF) tw_col[tid] = cconj(twiddle_n(p, 2 * (int64_t)ka * (c0 + 2 * tid)));
     }
     const float2 step_inv = cconj(twiddle_n(p, 2 * (int64_t)ka));   // inverse: conj W_M^ka, the same for the whole CTA
+    static_assert(F::NT_v % HALF == 0, "each thread keeps one column pair");
+    const int c2 = (tid & (HALF - 1)) * 2;       // this thread's column pair in every loop below
 #pragma unroll
-    for (int e = tid; e < NB * HALF; e += F::NT_v) {
-        const int i = e / HALF, c2 = (e - i * HALF) * 2;   // forward: i = b ; inverse: i = kb
+    for (int i = tid / HALF; i < NB; i += F::NT_v / HALF) {   // forward: i = b ; inverse: i = kb
         const int pos = DIR > 0 ? i : digit_pos_ct<F::LOGNB_v>(i);
         *reinterpret_cast<float4*>(&sm[lay(c2, pos)]) = T4[(base + ((int64_t)i << F::LOGNC_v) + c2) >> 1];
     }
@@ -143,9 +144,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
     if (DIR > 0) fft_fwd_ct<F::LOGNB_v, 0, true, LOGC, ColLayoutCt<LOGC>, F::LOGNB_v, F::NT_v>(sm, lay, tw_s, tid);
     else fft_inv_ct<F::LOGNB_v, CtPlan<F::LOGNB_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGNB_v, F::NT_v>(sm, lay, tw_s, tid);
 #pragma unroll 4
-    for (int e = tid; e < NB * HALF; e += F::NT_v) {
-        const int pos = e / HALF, c2 = (e - pos * HALF) * 2;
-        const int c = c0 + c2;
+    for (int pos = tid / HALF; pos < NB; pos += F::NT_v / HALF) {
         const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, pos)]);
         float2 a, b;
         int i;
@@ -309,17 +308,17 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p5(FftParams p) {
     const float4* T4 = reinterpret_cast<const float4*>(p.T);
     __shared__ float2 tw_s[NA];
     load_twiddles<F::LOGNA_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
+    static_assert(F::NT_v % HALF == 0, "each thread keeps one column pair");
+    const int c2 = (tid & (HALF - 1)) * 2;
 #pragma unroll
-    for (int e = tid; e < NA * HALF; e += F::NT_v) {
-        const int ka = e / HALF, c2 = (e - ka * HALF) * 2;
+    for (int ka = tid / HALF; ka < NA; ka += F::NT_v / HALF) {
         *reinterpret_cast<float4*>(&sm[lay(c2, digit_pos_ct<F::LOGNA_v>(ka))]) = T4[(((int64_t)ka << F::LOGNBC_v) + r0 + c2) >> 1];
     }
     __syncthreads();
     fft_inv_ct<F::LOGNA_v, CtPlan<F::LOGNA_v>::nst - 1, true, LOGC, ColLayoutCt<LOGC>, F::LOGNA_v, F::NT_v>(sm, lay, tw_s, tid);
     const bool out_aligned = (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
 #pragma unroll 4
-    for (int e = tid; e < NA * HALF; e += F::NT_v) {
-        const int a = e / HALF, c2 = (e - a * HALF) * 2;
+    for (int a = tid / HALF; a < NA; a += F::NT_v / HALF) {
         const int64_t j = ((int64_t)a << F::LOGNBC_v) + r0 + c2;
         const int64_t m0 = 2 * j;   // y[j] = r[2j] + i r[2j+1]: two adjacent columns = four consecutive lags
         if (m0 > p.m_hi || m0 + 3 < p.m_lo) continue;
