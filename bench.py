@@ -658,7 +658,8 @@ def main():
         with open(tp) as f:
             traffic = json.load(f).get("k_render_dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "k_render (amDemod+sig_to_image+downgradeImage fused)", "achieved": achieved,
-                "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "frac_of_spec_8000": achieved / 8000.0, "traffic": traffic,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_per_launch": render_ms,
                 "stage_ms_per_step": {"k_render": render_ms, "k_project+k_sync": stage_ms[1] / max(pushes, 1),
                                       "k_accumulate+carry": stage_ms[2] / max(pushes, 1)},
