@@ -179,6 +179,10 @@ int tsdr_chain_read_image(tsdr_chain* c, float* out_colmajor);
 int tsdr_chain_read_offsets(tsdr_chain* c, int* s_y, int* s_x, int max, int* n_frames);
 /* every published imageOut of the last buffer (needs TSDR_CHAIN_PUBLISH_ALL):
  * n_frames x 600 x 800, each column-major */
+/* Per frame of the last buffer: the maxima of the two sync tables, findmax(beta_x)[1] and findmax(beta_y)[1]
+ * (src/FrameSynchronisation.jl:66,76), and Sigma = sum of the filtered column / row projection (:96).  Their ratio
+ * to the squared mean projection is the blanking contrast a configuration search scores hypotheses with. */
+int tsdr_chain_read_scores(tsdr_chain* c, float* beta_x_max, float* beta_y_max, float* sigma_x, float* sigma_y, int max, int* n_frames);
 int tsdr_chain_read_published(tsdr_chain* c, float* out, int max_frames, int* n_frames);
 /* device pointers / stream, for collectives the host runs on the accumulator
  * (NCCL allreduce of partial frame sums) and for event timing.  The

@@ -67,6 +67,7 @@ SIGNATURES = {
     "tsdr_chain_flush": (C.c_int, [_vp]),
     "tsdr_chain_read_image": (C.c_int, [_vp, _vp]),
     "tsdr_chain_read_offsets": (C.c_int, [_vp, _vp, _vp, C.c_int, _ip]),
+    "tsdr_chain_read_scores": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _ip]),
     "tsdr_chain_read_published": (C.c_int, [_vp, _vp, C.c_int, _ip]),
     "tsdr_chain_accumulator": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "tsdr_chain_scale_accumulator": (C.c_int, [_vp, C.c_float]),

@@ -20,7 +20,7 @@ __all__ = [
     "calculate_autocorrelation", "zoom_autocorr", "getSpectrum", "getWelch", "getWaterfall", "findmax", "findmax_device", "findmax_windows_device", "sweep_refresh_hypotheses", "SyncXY", "vsync", "fullScale",
     "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
     "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
-    "Chain", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "TempestError", "RENDERING_SIZE",
+    "Chain", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "search_configuration", "blanking_contrast", "TempestError", "RENDERING_SIZE",
     "device_count", "set_device",
 ]
 
@@ -431,6 +431,16 @@ class Chain:
         k = min(n.value, max_frames)
         return sy[:k].copy(), sx[:k].copy()
 
+    def scores(self, max_frames=65536):
+        """per frame of the last buffer: (max beta_x, max beta_y, Sigma_x, Sigma_y) -- the maxima of the two sync tables
+        (src/FrameSynchronisation.jl:66,76) and the sums of the filtered projections (:96)"""
+        bx, by = np.zeros(max_frames, np.float32), np.zeros(max_frames, np.float32)
+        sx, sy = np.zeros(max_frames, np.float32), np.zeros(max_frames, np.float32)
+        n = C.c_int(0)
+        check(_lib.load().tsdr_chain_read_scores(self._h, _ptr(bx), _ptr(by), _ptr(sx), _ptr(sy), max_frames, C.byref(n)))
+        k = min(n.value, max_frames)
+        return bx[:k].copy(), by[:k].copy(), sx[:k].copy(), sy[:k].copy()
+
     def published(self, max_frames=None):
         """every intermediate imageOut of the last buffer (non_blocking_put!, src/GUI.jl:177)"""
         if max_frames is None:
@@ -599,6 +609,49 @@ def sweep_refresh_hypotheses(gamma_ptr, n_gamma, Fs, hypotheses=None, half_width
     for (r, lo, _), (val, idx) in zip(mine, found):
         k = lo + idx - 1                      # 1-based index into Gamma; the reference reads it as lag k/Fs
         out.append((float(r), float(val), 1.0 / (k / Fs), int(k)))
+    return out
+
+
+def blanking_contrast(beta_max, sigma, n):
+    """beta = ((Sigma - S_w)/(2(n-w)) + S_w/(2w))^2 at its maximum, relative to the value the same expression takes for a
+    flat projection (mean^2): 1 for a featureless image, larger the more a blanking band stands out"""
+    mean = np.asarray(sigma, np.float64) / n
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.asarray(beta_max, np.float64) / (mean * mean)
+
+
+def search_configuration(iq, Fs, candidates, frames=3, y_nudges=(0,), device=0, rank=0, world=1):
+    """render-and-score configuration search, replacing the click loop of the GUI (the list clicks of
+    src/GUI.jl:450-459 and the +-1 line nudges of :526-537).  Every hypothesis -- a VideoMode of `candidates`, its height
+    moved by each of `y_nudges` -- renders the first `frames` frames of the capture through the chain and is scored by the
+    blanking contrast of its sync tables: a raster with the right line count keeps the horizontal blanking bar vertical,
+    so the column projection has a sharp band and max(beta_x) stands far above its flat-image value; one line off and the
+    bar shears across the whole width.  Hypotheses are sharded round-robin over `world` ranks (no exchange on the data
+    path).  Returns [(score, VideoMode, contrast_x, contrast_y)] sorted best first.  There is no reference function to
+    compare with: tests check that synthetic captures of known modes are recovered."""
+    z, n = _iq(iq)
+    hyps = []
+    for cfg in candidates:
+        for dy in y_nudges:
+            hyps.append(VideoMode(cfg.width, cfg.height + dy, cfg.refresh))
+    out = []
+    for i, cfg in enumerate(hyps):
+        if i % world != rank:
+            continue
+        S = getImageDuration(cfg, Fs)
+        need = frames * S
+        if need > n or cfg.height < 2:
+            continue
+        ch = Chain(Fs, cfg, alpha=0.0, max_samples=need, device=device)
+        try:
+            ch.push(z[:need])
+            bx, by, sx, sy = ch.scores()
+        finally:
+            ch.close()
+        cx = float(np.median(blanking_contrast(bx, sx, RENDERING_SIZE[1])))
+        cy = float(np.median(blanking_contrast(by, sy, RENDERING_SIZE[0])))
+        out.append((cx * cy, cfg, cx, cy))
+    out.sort(key=lambda t: -t[0])
     return out
 
 

@@ -636,7 +636,7 @@ int tsdr_vsync_f32(tsdr_sync* s, const float* img_colmajor, int* s_y, int* s_x) 
     dim3 tg((kRenderH + 31) / 32, (kRenderW + 31) / 32), tb(32, 8);
     k_transpose<<<tg, tb>>>(s->d_img_cm, s->d_img, kRenderW, kRenderH);
     launch_sync_stage(s->d_img, 1, s->d_cv, s->d_ch, s->sp, 0);
-    k_sync_carry<<<1, 32>>>(s->d_best, 1, s->d_off, s->d_off + 1);
+    k_sync_carry<<<1, 32>>>(s->d_best, 1, s->d_off, s->d_off + 1, nullptr, nullptr);
     TSDR_CUDA(cudaGetLastError());
     int off[2];
     TSDR_CUDA(cudaMemcpy(off, s->d_off, sizeof(off), cudaMemcpyDeviceToHost));
@@ -703,6 +703,7 @@ struct tsdr_chain {
     float* d_cfv; float* d_cfh; float* d_sigma; unsigned int* d_tickets;
     unsigned long long* d_best;
     int* d_sy; int* d_sx;
+    float* d_bx; float* d_by;   // per frame: max of beta_x / beta_y
     int* d_fy; double* d_dy; double* d_kd; double* d_dx; int* d_win_lo; int* d_win_len;
     // optional per-kernel event timing
     bool profiling;
@@ -735,6 +736,8 @@ static void chain_free_frames(tsdr_chain* c) {
     cudaFree(c->d_best); c->d_best = nullptr;
     cudaFree(c->d_sy); c->d_sy = nullptr;
     cudaFree(c->d_sx); c->d_sx = nullptr;
+    cudaFree(c->d_bx); c->d_bx = nullptr;
+    cudaFree(c->d_by); c->d_by = nullptr;
 }
 
 static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
@@ -810,6 +813,8 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         TSDR_CUDA(cudaMalloc(&c->d_best, (size_t)(max_frames + 1) * 2 * 8));
         TSDR_CUDA(cudaMalloc(&c->d_sy, (size_t)max_frames * 4));
         TSDR_CUDA(cudaMalloc(&c->d_sx, (size_t)max_frames * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_bx, (size_t)max_frames * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_by, (size_t)max_frames * 4));
         TSDR_CUDA(cudaMemsetAsync(c->d_best, 0, (size_t)(max_frames + 1) * 2 * 8, c->stream));
         TSDR_CUDA(cudaMemcpyAsync(c->d_best + 1, &kBestInit, 8, cudaMemcpyHostToDevice, c->stream));
         TSDR_CUDA(cudaStreamSynchronize(c->stream));
@@ -925,7 +930,7 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
         else k_accumulate<false><<<kRenderH, kAccThreads, 0, st2>>>(ap);
         c->launches += 1;
     }
-    if (align) { k_sync_carry<<<1, 256, 0, st2>>>(c->d_best, nb, c->d_sy, c->d_sx); c->launches += 1; }
+    if (align) { k_sync_carry<<<1, 256, 0, st2>>>(c->d_best, nb, c->d_sy, c->d_sx, c->d_bx, c->d_by); c->launches += 1; }
     mark(st2);
     if (host_image) {
         // per-buffer delivery (non_blocking_put!(imageOut), GUI.jl:177): transpose to Julia layout and copy out, stream ordered
@@ -1219,6 +1224,23 @@ int tsdr_chain_read_offsets(tsdr_chain* c, int* s_y, int* s_x, int max, int* n_f
     if (n > 0 && s_y) TSDR_CUDA(cudaMemcpyAsync(s_y, c->d_sy, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (n > 0 && s_x) TSDR_CUDA(cudaMemcpyAsync(s_x, c->d_sx, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     TSDR_CUDA(cudaStreamSynchronize(c->stream));
+    return TSDR_OK;
+}
+
+int tsdr_chain_read_scores(tsdr_chain* c, float* beta_x_max, float* beta_y_max, float* sigma_x, float* sigma_y, int max, int* n_frames) {
+    TSDR_REQUIRE(c, "chain is NULL");
+    TSDR_REQUIRE(!(c->flags & TSDR_CHAIN_NO_ALIGN), "no sync search ran (TSDR_CHAIN_NO_ALIGN)");
+    TSDR_CUDA(cudaSetDevice(c->device));
+    { int rc = chain_join(c); if (rc) return rc; }
+    const int n = c->last_frames < max ? c->last_frames : max;
+    if (n_frames) *n_frames = c->last_frames;
+    if (n <= 0) return TSDR_OK;
+    std::vector<float> sg((size_t)2 * n);
+    if (beta_x_max) TSDR_CUDA(cudaMemcpyAsync(beta_x_max, c->d_bx, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (beta_y_max) TSDR_CUDA(cudaMemcpyAsync(beta_y_max, c->d_by, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    TSDR_CUDA(cudaMemcpyAsync(sg.data(), c->d_sigma, (size_t)2 * n * 4, cudaMemcpyDeviceToHost, c->stream));
+    TSDR_CUDA(cudaStreamSynchronize(c->stream));
+    for (int f = 0; f < n; ++f) { if (sigma_x) sigma_x[f] = sg[2 * f]; if (sigma_y) sigma_y[f] = sg[2 * f + 1]; }
     return TSDR_OK;
 }
 

@@ -197,6 +197,18 @@ function offsets(c::Chain, maxframes = 4096)
     return Int.(sy[1:k]), Int.(sx[1:k])
 end
 
+# per frame of the last buffer: (max beta_x, max beta_y, Sigma_x, Sigma_y) -- what a configuration search scores
+function scores(c::Chain, maxframes = 4096)
+    bx = zeros(Float32, maxframes); by = zeros(Float32, maxframes)
+    sx = zeros(Float32, maxframes); sy = zeros(Float32, maxframes)
+    n = Ref{Cint}(0)
+    GC.@preserve bx by sx sy check(ccall((:tsdr_chain_read_scores, LIB), Cint,
+                                         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cint}),
+                                         c.handle, pointer(bx), pointer(by), pointer(sx), pointer(sy), maxframes, n))
+    k = min(Int(n[]), maxframes)
+    return bx[1:k], by[1:k], sx[1:k], sy[1:k]
+end
+
 configure!(c::Chain, Fs, x_t, y_t, fv) = check(ccall((:tsdr_chain_configure, LIB), Cint,
                                                      (Ptr{Cvoid}, Cdouble, Cint, Cint, Cdouble), c.handle, Fs, x_t, y_t, fv))
 set_alpha!(c::Chain, α) = check(ccall((:tsdr_chain_set_alpha, LIB), Cint, (Ptr{Cvoid}, Cfloat), c.handle, α))

@@ -563,6 +563,36 @@ def test_two_host_threads_call_concurrently(synth):
     assert not errors, errors
 
 
+@pytest.mark.parametrize("Fs,mode", [(20.0e6, (1056, 628, 60.0)), (8.0e6, (800, 525, 70.0))])
+def test_search_configuration_recovers_line_count(synth, Fs, mode):
+    # SURVEY 8(f) rank 2 (no reference function: the GUI does this by hand, src/GUI.jl:450-459,526-537): among the
+    # table's modes at this refresh rate and +-3 line nudges of the true mode, the synthetic capture's own raster must
+    # score best, by a clear margin, and the per-frame scores must be what the oracle's sync tables give
+    x_t, y_t, fv = mode
+    S = orc.frame_samples(Fs, fv)
+    iq = synth.make_iq(3 * S + 11, Fs, x_t, y_t, fv, seed=31)
+    true = tsdr.VideoMode(x_t, y_t, fv)
+    table = [c for c in tsdr.allVideoConfigurations.values() if abs(c.refresh - fv) < 0.6 and c != true][:6]
+    nudged = [tsdr.VideoMode(x_t, y_t + d, fv) for d in (-3, -2, -1, 1, 2, 3)]
+    res = tsdr.search_configuration(iq, Fs, [true] + table + nudged, frames=3)
+    assert res[0][1] == true
+    assert res[0][0] > 1.8 * res[1][0]
+    halves = tsdr.search_configuration(iq, Fs, [true] + table + nudged, frames=3, rank=0, world=2) + \
+        tsdr.search_configuration(iq, Fs, [true] + table + nudged, frames=3, rank=1, world=2)
+    assert sorted(h[0] for h in halves) == sorted(r[0] for r in res)
+    # the raw scores are the maxima of the oracle's beta tables for the same frames
+    ch = tsdr.Chain(Fs, true, alpha=0.0, max_samples=3 * S)
+    ch.push(iq[: 3 * S])
+    bx, by, sgx, sgy = ch.scores()
+    ch.close()
+    so = orc.SyncXY()
+    for f in range(3):
+        env = orc.amDemod(iq[f * S:(f + 1) * S])
+        img = orc.downgradeImage(orc.sig_to_image(env, y_t, x_t))
+        orc.vsync(img, so)
+        assert bx[f] == np.float32(so.beta_x().max()) and by[f] == np.float32(so.beta_y().max())
+
+
 def test_per_function_calls_on_second_gpu():
     import torch
     if tsdr.device_count() < 2:
