@@ -20,7 +20,7 @@ __all__ = [
     "calculate_autocorrelation", "zoom_autocorr", "getSpectrum", "getWelch", "getWaterfall", "findmax", "findmax_device", "findmax_windows_device", "sweep_refresh_hypotheses", "SyncXY", "vsync", "fullScale",
     "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
     "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
-    "Chain", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "search_configuration", "blanking_contrast", "TempestError", "RENDERING_SIZE",
+    "Chain", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "search_configuration", "blanking_contrast", "auto_configure", "TempestError", "RENDERING_SIZE",
     "device_count", "set_device",
 ]
 
@@ -653,6 +653,35 @@ def search_configuration(iq, Fs, candidates, frames=3, y_nudges=(0,), device=0, 
         out.append((cx * cy, cfg, cx, cy))
     out.sort(key=lambda t: -t[0])
     return out
+
+
+def auto_configure(iq, Fs, frames=3, nudge=3, refresh_tol=1.0, delayRate=1 / 10, rate_min=50, rate_max=90, device=0,
+                   rank=0, world=1):
+    """The whole configuration workflow of the GUI without the clicks: the refresh rate from the autocorrelation peak
+    (extract_configuration, src/GUI.jl:49-88), the line count from the line-lag peak (production/investigate_data.jl:69-82)
+    and the closest table entry (find_closest_configuration) as the reference computes them; then search_configuration
+    at the measured refresh rate over that estimate AND over every table entry within refresh_tol Hz (the list the GUI
+    user clicks through, src/GUI.jl:450-459), each with its line count moved by -nudge..nudge lines (the manual +-1
+    clicks of :526-537) -- the line-lag heuristic alone locks onto a sub-multiple on some captures.
+    Returns (best VideoMode, fv, y_t estimate, table entry name, ranking)."""
+    z, n = _iq(iq)
+    power = abs2(z)
+    _, _, fv = extract_configuration(power, Fs, delayRate=delayRate, rate_min=rate_min, rate_max=rate_max)
+    Gamma, _ = calculate_autocorrelation(power, Fs, 0, delayRate)
+    y_hat = estimate_lines(Gamma, Fs, fv)
+    name = list(find_closest_configuration(y_hat, fv))[0]
+    entry = allVideoConfigurations[name]
+    y0 = _round(y_hat)
+    bases = [(entry.width, y0)] + [(c.width, c.height) for c in allVideoConfigurations.values() if abs(c.refresh - fv) < refresh_tol]
+    seen, cands = set(), []
+    for w, h in bases:
+        for d in range(-nudge, nudge + 1):
+            if h + d >= 2 and (w, h + d) not in seen:
+                seen.add((w, h + d))
+                cands.append(VideoMode(w, h + d, float(fv)))
+    ranking = search_configuration(z, Fs, cands, frames=frames, device=device, rank=rank, world=world)
+    best = ranking[0][1] if ranking else VideoMode(entry.width, y0, float(fv))
+    return best, float(fv), float(y_hat), name, ranking
 
 
 def estimate_lines(Gamma, Fs, fv, N=500):

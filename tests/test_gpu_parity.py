@@ -593,6 +593,19 @@ def test_search_configuration_recovers_line_count(synth, Fs, mode):
         assert bx[f] == np.float32(so.beta_x().max()) and by[f] == np.float32(so.beta_y().max())
 
 
+def test_auto_configure_end_to_end(synth):
+    # capture of a known mode -> refresh rate, line count and raster without any manual step.  The measured refresh
+    # rate may sit a few lines off (the card's line-to-line correlation), and the best line count then compensates:
+    # what must hold is the LINE RATE fv * y_t, to within one line
+    Fs, (x_t, y_t, fv) = 2.0e6, (1056, 628, 60.0)
+    iq = synth.make_iq(int(0.25 * Fs), Fs, x_t, y_t, fv, seed=21)
+    best, fv_hat, y_hat, name, ranking = tsdr.auto_configure(iq, Fs, frames=3, nudge=4)
+    assert abs(fv_hat - fv) < 0.5 and tsdr.allVideoConfigurations[name].refresh == 60.0
+    assert abs(best.height - y_t * fv / fv_hat) <= 1.0
+    assert ranking[0][0] > 1.5 * ranking[-1][0] and len(ranking) >= 9
+    assert best.height != tsdr.api._round(y_hat)      # on this capture the line-lag heuristic alone is off
+
+
 def test_per_function_calls_on_second_gpu():
     import torch
     if tsdr.device_count() < 2:
