@@ -147,6 +147,22 @@ __global__ void __launch_bounds__(kFastThreads, 3) k_fft_cols_ct(FftParams p) {
         }
         *reinterpret_cast<float4*>(&sm[lay(c2, j1)]) = v;  // (c2, c2+1) are adjacent and 16-byte aligned in this layout
     }
+    // W_M^(j2 k1) as in the three-level kernels: k1 = 16 kh + kl, one small table each for this CTA's column pairs,
+    // and the neighbouring column by the row's step W_M^k1 -- no global twiddle look-up per element
+    constexpr bool kTables = LOGA <= 10 && LOGA >= 4;
+    constexpr int TA = kTables ? A : 1;
+    __shared__ float2 tw_step[TA];
+    __shared__ float2 tw_kh[kTables ? A / 16 : 1][HALF];
+    __shared__ float2 tw_kl[16][HALF];
+    if (kTables) {
+        for (int k = tid; k < A; k += kFastThreads) tw_step[k] = twiddle_n(p, 2 * (int64_t)k);
+        for (int e = tid; e < (A / 16 + 16) * HALF; e += kFastThreads) {
+            const int q = e / HALF, jj = e - q * HALF;
+            const int64_t j2 = j2_0 + 2 * jj;
+            if (q < A / 16) tw_kh[q][jj] = twiddle_n(p, 2 * (int64_t)(16 * q) * j2);
+            else tw_kl[q - A / 16][jj] = twiddle_n(p, 2 * (int64_t)(q - A / 16) * j2);
+        }
+    }
     __syncthreads();
     fft_fwd_ct<LOGA, 0, true, LOGC>(sm, lay, p.twA, tid);
 #pragma unroll 4
@@ -155,8 +171,16 @@ __global__ void __launch_bounds__(kFastThreads, 3) k_fft_cols_ct(FftParams p) {
         const int k1 = digit_rev_ct<LOGA>(row);
         const int j2 = j2_0 + c2;
         const float4 sv = *reinterpret_cast<const float4*>(&sm[lay(c2, row)]);
-        const float2 a = cmul(make_float2(sv.x, sv.y), twiddle_n(p, 2 * (int64_t)j2 * k1));          // W_M^(j2 k1) = W_N^(2 j2 k1)
-        const float2 b = cmul(make_float2(sv.z, sv.w), twiddle_n(p, 2 * (int64_t)(j2 + 1) * k1));
+        float2 wa, wb;
+        if (kTables) {
+            wa = cmul(tw_kh[k1 >> 4][c2 >> 1], tw_kl[k1 & 15][c2 >> 1]);
+            wb = cmul(wa, tw_step[k1]);
+        } else {
+            wa = twiddle_n(p, 2 * (int64_t)j2 * k1);          // W_M^(j2 k1) = W_N^(2 j2 k1)
+            wb = twiddle_n(p, 2 * (int64_t)(j2 + 1) * k1);
+        }
+        const float2 a = cmul(make_float2(sv.x, sv.y), wa);
+        const float2 b = cmul(make_float2(sv.z, sv.w), wb);
         reinterpret_cast<float4*>(p.T)[(((int64_t)row << LOGB) + j2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
     }
 }
@@ -183,6 +207,23 @@ __device__ __forceinline__ void mid_body(const FftParams& p, float2* sm, int k1a
     constexpr int A = 1 << LOGA, B = 1 << LOGB, NR = 1 << LOGNB;
     const int rowa = digit_pos_ct<LOGA>(k1a), rowb = digit_pos_ct<LOGA>(k1b);
     const RowLayoutCt lay{B + (B >> 4) + 1};
+    // twiddles as products of small per-CTA tables (see the three-level kernels): the unpack twiddle W_N^(k1a + A k2)
+    // with k2 = 64 qh + ql, the write-back twiddle conj W_N^(2 k1 j2) with j2 = 64 jh + jl (jl even) and the step
+    // conj W_N^(2 k1) from one column to the next
+    static_assert(B >= 64, "row length");
+    __shared__ float2 tw_mh[B / 64], tw_ml[64];
+    __shared__ float2 tw_jh[2][B / 64], tw_jl[2][32], tw_st[2];
+    for (int q = tid; q < B / 64; q += kFastThreads) {
+        tw_mh[q] = twiddle_n(p, (int64_t)k1a + (((int64_t)64 * q) << LOGA));
+        tw_jh[0][q] = cconj(twiddle_n(p, 2 * (int64_t)k1a * (64 * q)));
+        tw_jh[1][q] = cconj(twiddle_n(p, 2 * (int64_t)k1b * (64 * q)));
+    }
+    if (tid < 64) tw_ml[tid] = twiddle_n(p, (int64_t)tid << LOGA);
+    if (tid < 32) {
+        tw_jl[0][tid] = cconj(twiddle_n(p, 2 * (int64_t)k1a * (2 * tid)));
+        tw_jl[1][tid] = cconj(twiddle_n(p, 2 * (int64_t)k1b * (2 * tid)));
+    }
+    if (tid < 2) tw_st[tid] = cconj(twiddle_n(p, 2 * (int64_t)(tid == 0 ? k1a : k1b)));
     for (int e = tid; e < NR * (B / 2); e += kFastThreads) {
         const int r = e >> (LOGB - 1), i2 = (e & (B / 2 - 1)) * 2;
         const float4 v = reinterpret_cast<const float4*>(p.T)[((((int64_t)(r == 0 ? rowa : rowb)) << LOGB) + i2) >> 1];
@@ -196,7 +237,7 @@ __device__ __forceinline__ void mid_body(const FftParams& p, float2* sm, int k1a
         for (int pos = tid; pos < B; pos += kFastThreads) {
             const int k2 = digit_rev_ct<LOGB>(pos);
             const int pos2 = digit_pos_ct<LOGB>(B - 1 - k2);
-            mid_pair(p, sm[lay(0, pos)], sm[lay(1, pos2)], (int64_t)k1a + ((int64_t)k2 << LOGA), sc);
+            mid_pair_w(sm[lay(0, pos)], sm[lay(1, pos2)], cmul(tw_mh[k2 >> 6], tw_ml[k2 & 63]), sc);
         }
     } else if (k1a == 0) {
         for (int k2 = tid; k2 <= B / 2; k2 += kFastThreads) {
@@ -209,23 +250,23 @@ __device__ __forceinline__ void mid_body(const FftParams& p, float2* sm, int k1a
             }
             const int pos2 = digit_pos_ct<LOGB>(B - k2);
             float2 a = sm[lay(0, pos)], b = sm[lay(0, pos2)];
-            mid_pair(p, a, b, (int64_t)k2 << LOGA, sc);
+            mid_pair_w(a, b, cmul(tw_mh[k2 >> 6], tw_ml[k2 & 63]), sc);
             sm[lay(0, pos)] = a;
             if (pos2 != pos) sm[lay(0, pos2)] = b;
         }
     } else {  // k1 = A/2: k2 <-> B-1-k2
         for (int k2 = tid; k2 < B / 2; k2 += kFastThreads) {
             const int pos = digit_pos_ct<LOGB>(k2), pos2 = digit_pos_ct<LOGB>(B - 1 - k2);
-            mid_pair(p, sm[lay(0, pos)], sm[lay(0, pos2)], (int64_t)k1a + ((int64_t)k2 << LOGA), sc);
+            mid_pair_w(sm[lay(0, pos)], sm[lay(0, pos2)], cmul(tw_mh[k2 >> 6], tw_ml[k2 & 63]), sc);
         }
     }
     __syncthreads();
     fft_inv_ct<LOGB, CtPlan<LOGB>::nst - 1, false, LOGNB>(sm, lay, p.twB, tid);
     for (int e = tid; e < NR * (B / 2); e += kFastThreads) {
         const int r = e >> (LOGB - 1), j2 = (e & (B / 2 - 1)) * 2;
-        const int k1 = r == 0 ? k1a : k1b;
-        const float2 a = cmul(sm[lay(r, j2)], cconj(twiddle_n(p, 2 * (int64_t)j2 * k1)));
-        const float2 b = cmul(sm[lay(r, j2 + 1)], cconj(twiddle_n(p, 2 * (int64_t)(j2 + 1) * k1)));
+        const float2 wa = cmul(tw_jh[r][j2 >> 6], tw_jl[r][(j2 & 63) >> 1]);
+        const float2 a = cmul(sm[lay(r, j2)], wa);
+        const float2 b = cmul(sm[lay(r, j2 + 1)], cmul(wa, tw_st[r]));
         reinterpret_cast<float4*>(p.U)[((((int64_t)(r == 0 ? rowa : rowb)) << LOGB) + j2) >> 1] = make_float4(a.x, a.y, b.x, b.y);
     }
     (void)A;
