@@ -41,3 +41,25 @@ def test_zoom_and_conversions():
     assert tsdr.delay2yt(1 / (60 * 1125), 60) == 1125 and tsdr.yt2index(1125, 20e6, 60) == 296
     assert abs(tsdr.yt2delay(1125, 60) - 1 / 67500) < 1e-18
     assert tsdr.RENDERING_SIZE == (600, 800)
+
+
+def test_spectrum_axes_and_contrast_helpers():
+    # host arithmetic of the GetSpectrum.jl wrappers (src/GetSpectrum.jl:26,46,63-64) and of the search score
+    from tempestsdr_b200 import api
+    N, fs = 10, 4.0
+    assert np.allclose(api._freq_axis(N, fs), [((k / N) - 0.5) * fs for k in range(N)])
+    assert api._freq_axis(1024, 1.0)[512] == 0.0 and api._freq_axis(1024, 1.0)[0] == -0.5
+    # flat projection c = m: Sigma = n m; the reference's beta for it is (m/2 + m/2)^2 = m^2 -> contrast 1
+    n, m = 800, 3.5
+    assert np.allclose(api.blanking_contrast([m * m], [n * m], n), 1.0)
+    c = api.blanking_contrast([4.0, 0.0], [10.0, 0.0], 5)       # mean 2 -> 1.0 ; empty frame -> nan, not an exception
+    assert c[0] == 1.0 and np.isnan(c[1])
+
+
+def test_shard_helpers_cover_every_hypothesis_once():
+    from tempestsdr_b200 import parallel
+    for n, w in [(13, 8), (80, 8), (5, 2), (3, 4)]:
+        seen = sorted(sum((parallel.shard_round_robin(n, w, r) for r in range(w)), []))
+        assert seen == list(range(n))
+        blocks = [parallel.shard_contiguous(n, w, r) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
