@@ -40,7 +40,8 @@ typedef enum {
     TSDR_ERR_CUDA = -2,         /* CUDA runtime error, or no device */
     TSDR_ERR_NOMEM = -3,
     TSDR_ERR_UNSUPPORTED = -4,  /* configuration outside what the kernels handle */
-    TSDR_ERR_BOUNDS = -5        /* src/Autocorrelations.jl:30 BoundsError (signal shorter than indexMax) */
+    TSDR_ERR_BOUNDS = -5,       /* src/Autocorrelations.jl:30 BoundsError (signal shorter than indexMax) */
+    TSDR_ERR_NCCL = -6          /* NCCL returned an error (multi-GPU combine) */
 } tsdr_status;
 
 int tsdr_version(void);
@@ -200,6 +201,39 @@ int tsdr_chain_launch_count(tsdr_chain* c, uint64_t* count);
 int tsdr_chain_set_profiling(tsdr_chain* c, int enable);
 int tsdr_chain_kernel_times(tsdr_chain* c, float ms[TSDR_CHAIN_STAGES], uint64_t pushes[1]);
 int tsdr_chain_destroy(tsdr_chain* c);
+
+/* ---- multi-GPU combine of a long integration (BASELINE cfg 5) ------------------------------------
+ * The recurrence imageOut .= a*imageOut .+ (1-a)*image_mat (src/GUI.jl:175) is linear, so a 1000-frame integration
+ * shards into contiguous frame blocks, one per GPU: rank g runs its block from a zero accumulator (primed with
+ * the frame before the block, tsdr_chain_prime_*), and ONE all-reduce sums the partial accumulators, each
+ * multiplied by its tail weight a^(frames after the block) inside the collective (NCCL PreMulSum over NVLink).
+ * NCCL is bound at run time (dlopen libnccl.so.2, TEMPEST_B200_NCCL overrides); without it these calls return
+ * TSDR_ERR_UNSUPPORTED.  One communicator per GPU: either one process per GPU (rank 0 creates the id, the host
+ * distributes its 128 bytes, every rank calls tsdr_comm_init_rank), or one process driving several GPUs
+ * (tsdr_comm_init_all; collectives issued from one thread go between tsdr_comm_group_start/end). */
+#define TSDR_COMM_ID_BYTES 128
+typedef struct tsdr_comm tsdr_comm;
+int tsdr_comm_available(int* nccl_version);                       /* TSDR_OK when NCCL could be loaded */
+int tsdr_comm_get_unique_id(unsigned char id[TSDR_COMM_ID_BYTES]);
+int tsdr_comm_init_rank(tsdr_comm** out, int device, int nranks, int rank, const unsigned char id[TSDR_COMM_ID_BYTES]);
+int tsdr_comm_init_all(tsdr_comm** out /* [n_devices] */, int n_devices, const int* devices /* NULL: 0..n-1 */);
+int tsdr_comm_info(const tsdr_comm* c, int* device, int* nranks, int* rank, uint64_t* collectives);
+int tsdr_comm_group_start(void);
+int tsdr_comm_group_end(void);
+/* imageOut <- sum over ranks of weight_rank * imageOut_rank, in place on every rank, asynchronous on the chain's
+ * stream (after everything the chain has queued).  weight = a^(frames after this rank's block); 1 for plain sums. */
+int tsdr_chain_allreduce(tsdr_chain* c, tsdr_comm* comm, float weight);
+/* One rank's share of a sharded integration queued by ONE call (nothing blocks): reset, prime with the halo frame
+ * (the frame before the block; NULL for the first block), push the block's device buffers in order, combine.
+ * comm == NULL or a 1-rank communicator: no collective, the accumulator is only scaled by weight. */
+int tsdr_chain_integrate_device(tsdr_chain* c, const float* halo_dev, size_t halo_samples, const float* const* bufs_dev,
+                                const size_t* n_samples, int n_bufs, tsdr_comm* comm, float weight, int* n_frames);
+/* the same on any device vector of n floats (stream: cudaStream_t or NULL) */
+int tsdr_comm_allreduce_f32(tsdr_comm* c, float* buf_dev, size_t n, float weight, void* stream);
+/* every rank contributes bytes_per_rank bytes, every rank receives nranks*bytes_per_rank (rank order): the
+ * (score, lag) pairs of a sharded hypothesis sweep (BASELINE cfg 4) */
+int tsdr_comm_allgather(tsdr_comm* c, const void* send_dev, void* recv_dev, size_t bytes_per_rank, void* stream);
+int tsdr_comm_destroy(tsdr_comm* c);
 
 /* ---- GetSpectrum.jl: the spectra used to find the leakage carrier, on the same FFT engine ----
  * getSpectrum(fs, sig; N) (src/GetSpectrum.jl:21-30): y[N] = 10*log10.(abs2.(fftshift(fft(sig[1:N])))) of a ComplexF32

@@ -307,11 +307,11 @@ void orc_zoom_window(size_t n_gamma, double Fs, double rate_min, double rate_max
     *pos_min = a; *pos_max = b;
 }
 
-size_t orc_findmax(const float* v, size_t n) { /* Base.findmax: first max, NaN dominates */
-    size_t best = 0;
+size_t orc_findmax(const float* v, size_t n) { /* Base.findmax: first maximum under isless (reduce.jl _rf_findmax): */
+    size_t best = 0;                               /* NaN dominates, -0.0 sorts below +0.0 */
     for (size_t i = 0; i < n; ++i) {
         if (isnan(v[i])) return i;
-        if (v[i] > v[best]) best = i;
+        if (v[i] > v[best] || (v[i] == v[best] && signbit(v[best]) && !signbit(v[i]))) best = i;
     }
     return best;
 }

@@ -76,6 +76,19 @@ SIGNATURES = {
     "tsdr_chain_set_profiling": (C.c_int, [_vp, C.c_int]),
     "tsdr_chain_kernel_times": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "tsdr_chain_destroy": (C.c_int, [_vp]),
+    "tsdr_comm_available": (C.c_int, [_ip]),
+    "tsdr_comm_get_unique_id": (C.c_int, [_vp]),
+    "tsdr_comm_init_rank": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _vp]),
+    "tsdr_comm_init_all": (C.c_int, [C.POINTER(_vp), C.c_int, _ip]),
+    "tsdr_comm_info": (C.c_int, [_vp, _ip, _ip, _ip, C.POINTER(C.c_uint64)]),
+    "tsdr_comm_group_start": (C.c_int, []),
+    "tsdr_comm_group_end": (C.c_int, []),
+    "tsdr_chain_allreduce": (C.c_int, [_vp, _vp, C.c_float]),
+    "tsdr_chain_integrate_device": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(_vp), C.POINTER(C.c_size_t), C.c_int, _vp,
+                                              C.c_float, _ip]),
+    "tsdr_comm_allreduce_f32": (C.c_int, [_vp, _vp, C.c_size_t, C.c_float, _vp]),
+    "tsdr_comm_allgather": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "tsdr_comm_destroy": (C.c_int, [_vp]),
     "tsdr_get_spectrum_f32": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp]),
     "tsdr_get_welch_f32": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp]),
     "tsdr_get_waterfall_f32": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp]),

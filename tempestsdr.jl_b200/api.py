@@ -20,7 +20,7 @@ __all__ = [
     "calculate_autocorrelation", "zoom_autocorr", "getSpectrum", "getWelch", "getWaterfall", "findmax", "findmax_device", "findmax_windows_device", "sweep_refresh_hypotheses", "SyncXY", "vsync", "fullScale",
     "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
     "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
-    "Chain", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "search_configuration", "blanking_contrast", "auto_configure", "TempestError", "RENDERING_SIZE",
+    "Chain", "Comm", "comm_available", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "search_configuration", "blanking_contrast", "auto_configure", "TempestError", "RENDERING_SIZE",
     "device_count", "set_device",
 ]
 
@@ -163,8 +163,11 @@ def zoom_autocorr(Gamma, Fs, rate_min=20, rate_max=100):
     N = len(Gamma)
     pos_rate_min = min(_round(1 / rate_max * Fs), N)
     pos_rate_max = min(_round(1 / rate_min * Fs), N)
+    if pos_rate_min < 1:   # the reference indexes Gamma[0:...] here: BoundsError
+        raise IndexError("BoundsError: zoom_autocorr window starts at index %d (rate_max %g too large for Fs %g)"
+                         % (pos_rate_min, rate_max, Fs))
     xAx = np.arange(pos_rate_min, pos_rate_max + 1, dtype=np.float64) / Fs
-    return 1.0 / xAx, np.asarray(Gamma)[pos_rate_min - 1: pos_rate_max]
+    return 1.0 / xAx, np.asarray(Gamma)[pos_rate_min - 1: max(pos_rate_max, pos_rate_min - 1)]
 
 
 def _freq_axis(n, fs):  # collect(((0:N-1)./N .- 0.5)*fs)
@@ -451,6 +454,18 @@ class Chain:
         k = min(n.value, max_frames)
         return buf[:k].transpose(0, 2, 1)  # each frame column-major -> [row, col] view
 
+    def integrate_device(self, halo_ptr, halo_samples, buf_ptrs, buf_samples, comm=None, weight=1.0):
+        """one rank's share of a sharded integration in ONE call: reset, prime with the halo frame (0: none), push the
+        device buffers in order, combine over `comm` (None: scale only).  Returns the frames pushed."""
+        n = len(buf_ptrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[int(p) for p in buf_ptrs])
+        cnt = (C.c_size_t * max(n, 1))(*[int(v) for v in buf_samples])
+        nf = C.c_int(0)
+        check(_lib.load().tsdr_chain_integrate_device(self._h, C.c_void_p(halo_ptr) if halo_ptr else None, int(halo_samples),
+                                                      ptrs, cnt, n, comm._h if comm is not None else None, float(weight),
+                                                      C.byref(nf)))
+        return nf.value
+
     def accumulator_ptr(self):
         p, n = C.c_void_p(), C.c_size_t(0)
         check(_lib.load().tsdr_chain_accumulator(self._h, C.byref(p), C.byref(n)))
@@ -482,6 +497,70 @@ class Chain:
     def close(self):
         if getattr(self, "_h", None):
             _lib.load().tsdr_chain_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def comm_available():
+    """NCCL version the library could bind at run time (dlopen), or 0"""
+    v = C.c_int(0)
+    rc = _lib.load().tsdr_comm_available(C.byref(v))
+    return v.value if rc == 0 else 0
+
+
+class Comm:
+    """One NCCL communicator rank behind the C ABI (tsdr_comm_*): combines the partial imageOut accumulators of a
+    sharded integration (src/GUI.jl:175 is linear in the frames).  One process per GPU:
+
+        uid = Comm.unique_id() on rank 0  ->  distribute the 128 bytes  ->  Comm(uid, world, rank, device)
+    """
+
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * Comm.ID_BYTES)()
+        check(_lib.load().tsdr_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, uid, nranks, rank, device=0):
+        if len(uid) != Comm.ID_BYTES:
+            raise ValueError("unique id must be %d bytes" % Comm.ID_BYTES)
+        h = C.c_void_p()
+        buf = (C.c_ubyte * Comm.ID_BYTES).from_buffer_copy(uid)
+        check(_lib.load().tsdr_comm_init_rank(C.byref(h), int(device), int(nranks), int(rank), buf))
+        self._h, self.nranks, self.rank, self.device = h, int(nranks), int(rank), int(device)
+
+    @classmethod
+    def from_torch_distributed(cls, device, group=None):
+        """bootstrap over an initialised torch.distributed group (plumbing only: 128 bytes, once)"""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(box[0], world, rank, device)
+
+    def allreduce_chain(self, chain, weight=1.0):
+        """imageOut <- sum over ranks of weight_rank * imageOut_rank, asynchronous on the chain's stream"""
+        check(_lib.load().tsdr_chain_allreduce(chain._h, self._h, float(weight)))
+
+    def allreduce(self, ptr, n_floats, weight=1.0, stream=None):
+        check(_lib.load().tsdr_comm_allreduce_f32(self._h, C.c_void_p(ptr), int(n_floats), float(weight),
+                                                  C.c_void_p(stream) if stream else None))
+
+    def allgather(self, send_ptr, recv_ptr, bytes_per_rank, stream=None):
+        check(_lib.load().tsdr_comm_allgather(self._h, C.c_void_p(send_ptr), C.c_void_p(recv_ptr), int(bytes_per_rank),
+                                              C.c_void_p(stream) if stream else None))
+
+    def collectives(self):
+        v = C.c_uint64(0)
+        check(_lib.load().tsdr_comm_info(self._h, None, None, None, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().tsdr_comm_destroy(self._h)
             self._h = None
 
     __del__ = close

@@ -23,6 +23,7 @@ UNITS = [
     ("tsdr_core.cu", ["-fmad=false"]),
     ("tsdr_fft.cu", ["-fmad=true"]),
     ("tsdr_ring.cu", []),
+    ("tsdr_comm.cu", []),
 ]
 
 

@@ -29,9 +29,46 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 // --------------------------------------------------------------- scratch ----
 static thread_local int g_device = 0;
 struct Scratch { void* p = nullptr; size_t bytes = 0; int device = -1; };
-static thread_local Scratch g_scratch[8];
+// the destructor runs when the owning host thread exits (a Julia worker that dies does not leak device memory);
+// at process exit the runtime may already be unloading, cudaFree then fails harmlessly
+struct ScratchSet {
+    Scratch s[8];
+    ~ScratchSet() {
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return; }
+        for (Scratch& e : s)
+            if (e.p) { if (cudaSetDevice(e.device) == cudaSuccess) cudaFree(e.p); e.p = nullptr; }
+        cudaSetDevice(prev);
+        cudaGetLastError();
+    }
+};
+static thread_local ScratchSet g_scratch;
 
 int current_device() { return g_device; }
+
+int DeviceScope::enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != device) TSDR_CUDA(cudaSetDevice(device));
+    cur = device;
+    return TSDR_OK;
+}
+
+int DeviceScope::enter_default() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); libtempest_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return TSDR_ERR_CUDA;
+    }
+    return enter(g_device);
+}
+
+DeviceScope::~DeviceScope() {
+    if (prev >= 0 && cur >= 0 && prev != cur) { cudaSetDevice(prev); cudaGetLastError(); }
+}
 
 int ensure_device() {
     int n = 0;
@@ -46,18 +83,41 @@ int ensure_device() {
     return TSDR_OK;
 }
 
+cudaError_t allow_max_dynamic_smem(const void* kernel) {
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void*>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& d : done) if (d.first == dev && d.second == kernel) return cudaSuccess;
+    int optin = 0;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    const int room = optin - (int)fa.sharedSizeBytes;   // static shared memory counts against the same limit
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, room);
+    if (e == cudaSuccess) done.emplace_back(dev, kernel);
+    return e;
+}
+
 int scratch(int slot, size_t bytes, void** ptr) {
-    Scratch& s = g_scratch[slot];
+    Scratch& s = g_scratch.s[slot];
+    int dev = g_device;
+    cudaGetDevice(&dev);
     if (bytes < 256) bytes = 256;
-    if (s.p && (s.bytes < bytes || s.device != g_device)) {
-        cudaFree(s.p);
+    if (s.p && (s.bytes < bytes || s.device != dev)) {
+        if (s.device != dev) { cudaSetDevice(s.device); cudaFree(s.p); cudaSetDevice(dev); }
+        else cudaFree(s.p);
         s.p = nullptr; s.bytes = 0;
     }
     if (!s.p) {
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&s.p, want);
         if (e != cudaSuccess) { s.p = nullptr; set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); cudaGetLastError(); return TSDR_ERR_NOMEM; }
-        s.bytes = want; s.device = g_device;
+        s.bytes = want; s.device = dev;
     }
     *ptr = s.p;
     return TSDR_OK;
@@ -214,14 +274,13 @@ __global__ void __launch_bounds__(kEwThreads) k_downgrade(const float* __restric
 __device__ __forceinline__ unsigned int ordered_bits(float v) {
     if (v != v) return 0xffffffffu;                      // NaN above everything
     const unsigned int b = __float_as_uint(v);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);   // monotone map of the float order (-0 < +0 is harmless: isequal order)
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);   // monotone map of the isless order (-0.0 below +0.0)
 }
 __global__ void __launch_bounds__(kEwThreads) k_findmax_partial(const float* __restrict__ v, size_t n, unsigned long long* __restrict__ part) {
     __shared__ unsigned long long sm[kEwThreads / 32];
     unsigned long long key = 0ull;
     for (size_t i = (size_t)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kEwThreads) {
-        float x = v[i];
-        if (x == 0.0f) x = 0.0f;  // findmax treats -0.0 == 0.0 for '<': keep the first of equal values
+        const float x = v[i];   // Base.findmax compares with isless: -0.0 sorts below +0.0 (ordered_bits keeps that)
         const unsigned long long k = ((unsigned long long)ordered_bits(x) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)i);
         key = k > key ? k : key;
     }
@@ -248,8 +307,7 @@ __global__ void __launch_bounds__(kEwThreads) k_findmax_windows(const float* __r
     const unsigned int lo = w.lo[blockIdx.y], len = w.len[blockIdx.y];
     unsigned long long key = 0ull;
     for (unsigned int i = blockIdx.x * kEwThreads + threadIdx.x; i < len; i += gridDim.x * kEwThreads) {
-        float x = v[(size_t)lo + i];
-        if (x == 0.0f) x = 0.0f;
+        const float x = v[(size_t)lo + i];
         const unsigned long long k = ((unsigned long long)ordered_bits(x) << 32) | (unsigned long long)(0xffffffffu - i);
         key = k > key ? k : key;
     }
@@ -310,7 +368,7 @@ int tsdr_set_device(int device) {
 static int demod_common(int mode, const float* iq, float* out, size_t n) {
     TSDR_REQUIRE(n == 0 || (iq && out), "NULL buffer");
     if (n == 0) return TSDR_OK;
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     void *d_in, *d_out;
     if ((rc = scratch(0, n * 8 + 16, &d_in)) || (rc = scratch(1, n * 4 + 16, &d_out))) return rc;
     TSDR_CUDA(cudaMemcpyAsync(d_in, iq, n * 8, cudaMemcpyHostToDevice, 0));
@@ -329,7 +387,7 @@ int tsdr_fm_demod_f32(const float* iq, float* out, size_t n) { return demod_comm
 int tsdr_invert_am_demod_f32(const float* iq, float* out, size_t n) {
     TSDR_REQUIRE(n == 0 || (iq && out), "NULL buffer");
     TSDR_REQUIRE(n > 0, "maximum of an empty collection (ArgumentError in the reference)");
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     void *d_in, *d_out, *d_part;
     const int parts = 1024;
     if ((rc = scratch(0, n * 8, &d_in)) || (rc = scratch(1, n * 4, &d_out)) || (rc = scratch(2, parts * 8, &d_part))) return rc;
@@ -346,7 +404,7 @@ int tsdr_invert_am_demod_f32(const float* iq, float* out, size_t n) {
 
 int tsdr_full_scale_f32(const float* in, float* out, size_t n) {
     TSDR_REQUIRE(n > 0 && in && out, "empty or NULL buffer");
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     void *d_in, *d_out, *d_part;
     const int parts = 1024;
     if ((rc = scratch(0, n * 4, &d_in)) || (rc = scratch(1, n * 4, &d_out)) || (rc = scratch(2, parts * 8, &d_part))) return rc;
@@ -365,7 +423,7 @@ int tsdr_naive_resampler_f32(float* out, const float* in, size_t n, int up) {
     TSDR_REQUIRE(up >= 1, "upCoeff must be >= 1");
     TSDR_REQUIRE(n == 0 || (in && out), "NULL buffer");
     if (n == 0) return TSDR_OK;
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     void *d_in, *d_out;
     const size_t n_out = n * (size_t)up;
     if ((rc = scratch(0, n * 4, &d_in)) || (rc = scratch(1, n_out * 4, &d_out))) return rc;
@@ -381,7 +439,7 @@ int tsdr_sig_to_image_f32(const float* sig, size_t n_sig, int y_t, int x_t, floa
     TSDR_REQUIRE(y_t >= 1 && x_t >= 1 && n_sig >= 2, "need y_t, x_t >= 1 and at least 2 samples");
     const size_t P = (size_t)y_t * (size_t)x_t;
     TSDR_REQUIRE(P < ((size_t)1 << 31), "image too large");
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     void *d_in, *d_out;
     if ((rc = scratch(0, n_sig * 4, &d_in)) || (rc = scratch(1, P * 4, &d_out))) return rc;
     TSDR_CUDA(cudaMemcpyAsync(d_in, sig, n_sig * 4, cudaMemcpyHostToDevice, 0));
@@ -396,7 +454,7 @@ int tsdr_sig_to_image_f32(const float* sig, size_t n_sig, int y_t, int x_t, floa
 int tsdr_downgrade_f32(const float* img_colmajor, int y_t, int x_t, float* out_colmajor) {
     TSDR_REQUIRE(img_colmajor && out_colmajor, "NULL buffer");
     TSDR_REQUIRE(y_t >= 2 && x_t >= 2, "image must be at least 2x2");
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     const size_t P = (size_t)y_t * (size_t)x_t;
     void *d_in, *d_out;
     if ((rc = scratch(0, P * 4, &d_in)) || (rc = scratch(1, (size_t)kRenderN * 4, &d_out))) return rc;
@@ -412,7 +470,7 @@ int tsdr_downgrade_f32(const float* img_colmajor, int y_t, int x_t, float* out_c
 int tsdr_findmax_f32(const float* v, size_t n, float* value, size_t* index1) {
     TSDR_REQUIRE(v && n > 0, "findmax of an empty collection");
     TSDR_REQUIRE(n < 0xffffffffull, "vector too long");
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     void *d_in, *d_part;
     const int parts = 512;
     if ((rc = scratch(0, n * 4, &d_in)) || (rc = scratch(2, parts * 8, &d_part))) return rc;
@@ -438,7 +496,7 @@ int tsdr_findmax_windows_dev_f32(const float* v_dev, int n_windows, const size_t
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, v_dev) == cudaSuccess && at.type == cudaMemoryTypeDevice) g_device = at.device;
     else cudaGetLastError();
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     void* d_scr;
     if ((rc = scratch(2, (size_t)kMaxWindows * (kWindowParts * 8 + 8) + 16, &d_scr))) return rc;
@@ -476,7 +534,7 @@ int tsdr_findmax_dev_f32(const float* v_dev, size_t n, float* value, size_t* ind
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, v_dev) == cudaSuccess && at.type == cudaMemoryTypeDevice) g_device = at.device;
     else cudaGetLastError();
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     void* d_part;
     const int parts = 512;
     if ((rc = scratch(2, parts * 8 + 16, &d_part))) return rc;
@@ -530,7 +588,7 @@ __global__ void __launch_bounds__(256) k_selftest_hypot(unsigned long long n, un
 
 extern "C" int tsdr_selftest_hypot(uint64_t n, uint64_t seed, uint64_t* mismatches) {
     TSDR_REQUIRE(mismatches, "mismatches is NULL");
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     void* d = nullptr;
     if ((rc = scratch(3, 8, &d))) return rc;
     TSDR_CUDA(cudaMemset(d, 0, 8));
@@ -582,7 +640,7 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     TSDR_REQUIRE(out, "out is NULL");
     TSDR_REQUIRE(n_y == kRenderH && n_x == kRenderW,
                  "SyncXY is only built for the %dx%d rendering size (src/GUI.jl:10), got %dx%d", kRenderH, kRenderW, n_y, n_x);
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     tsdr_sync* s = new (std::nothrow) tsdr_sync();
     if (!s) return TSDR_ERR_NOMEM;
     memset(s, 0, sizeof(*s));
@@ -597,7 +655,7 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     if (e == cudaSuccess) e = cudaMalloc(&s->d_img_cm, (size_t)kRenderN * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_img, (size_t)kRenderN * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cv, (size_t)kBands * n_x * 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProjSmem);
+    if (e == cudaSuccess) e = allow_max_dynamic_smem(k_project);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_ch, n_y * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cfv, n_x * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cfh, n_y * 4);
@@ -630,7 +688,7 @@ int tsdr_sync_bounds(const tsdr_sync* s, int* wmin_y, int* wmax_y, int* wmin_x, 
 
 int tsdr_vsync_f32(tsdr_sync* s, const float* img_colmajor, int* s_y, int* s_x) {
     TSDR_REQUIRE(s && img_colmajor && s_y && s_x, "NULL argument");
-    TSDR_CUDA(cudaSetDevice(s->device));
+    TSDR_DEVICE(s->device);
     TSDR_CUDA(cudaMemcpyAsync(s->d_img_cm, img_colmajor, (size_t)kRenderN * 4, cudaMemcpyHostToDevice, 0));
     // column-major 600x800 == row-major 800x600 -> scan order 600x800
     dim3 tg((kRenderH + 31) / 32, (kRenderW + 31) / 32), tb(32, 8);
@@ -646,7 +704,7 @@ int tsdr_vsync_f32(tsdr_sync* s, const float* img_colmajor, int* s_y, int* s_x) 
 
 int tsdr_sync_get_beta(tsdr_sync* s, float* beta_x, float* beta_y) {
     TSDR_REQUIRE(s, "sync is NULL");
-    TSDR_CUDA(cudaSetDevice(s->device));
+    TSDR_DEVICE(s->device);
     const size_t nbx = (size_t)(1 + s->sp.wmax_x - s->sp.wmin_x) * s->n_x, nby = (size_t)(1 + s->sp.wmax_y - s->sp.wmin_y) * s->n_y;
     if (beta_x) TSDR_CUDA(cudaMemcpy(beta_x, s->d_beta_x, nbx * 4, cudaMemcpyDeviceToHost));
     if (beta_y) TSDR_CUDA(cudaMemcpy(beta_y, s->d_beta_y, nby * 4, cudaMemcpyDeviceToHost));
@@ -655,7 +713,7 @@ int tsdr_sync_get_beta(tsdr_sync* s, float* beta_x, float* beta_y) {
 
 int tsdr_sync_destroy(tsdr_sync* s) {
     if (!s) return TSDR_OK;
-    cudaSetDevice(s->device);
+    TSDR_DEVICE(s->device);
     cudaFree(s->d_img_cm); cudaFree(s->d_img); cudaFree(s->d_cv); cudaFree(s->d_ch);
     cudaFree(s->d_cfv); cudaFree(s->d_cfh); cudaFree(s->d_sigma); cudaFree(s->d_tickets);
     cudaFree(s->d_beta_x); cudaFree(s->d_beta_y); cudaFree(s->d_best); cudaFree(s->d_off);
@@ -797,7 +855,7 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     const int max_frames = (int)(c->max_samples / (size_t)S);
     TSDR_REQUIRE(max_frames >= 1, "max_samples (%zu) holds no complete frame of %lld samples", c->max_samples, (long long)S);
 
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     if (max_frames > c->max_frames || !c->d_frames2[0]) {
         chain_free_frames(c);
         TSDR_CUDA(cudaMalloc(&c->d_frames2[0], (size_t)max_frames * kRenderN * 4));
@@ -849,12 +907,11 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     rp.fx_first = fx[0]; rp.fx_last = fx[kRenderW - 1];
     rp.rows_per_cta = G;
     rp.frames = nullptr;  // set per push
-    TSDR_CUDA(cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TSDR_CUDA(allow_max_dynamic_smem(k_render<false>));
     // Int16 input: the raw window (4 bytes per sample) sits behind the envelope region instead of under it
     c->smem_bytes_i16 = (size_t)(win + 8) * 12;
-    if (c->smem_bytes_i16 <= 200 * 1024)
-        TSDR_CUDA(cudaFuncSetAttribute(k_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes_i16));
-    TSDR_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kProjSmem));
+    TSDR_CUDA(allow_max_dynamic_smem(k_render<true>));
+    TSDR_CUDA(allow_max_dynamic_smem(k_project));
     SyncParams& sp = c->sp;
     gaussian_taps(sp.h);
     sp.n_x = kRenderW; sp.n_y = kRenderH;
@@ -960,6 +1017,7 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
     if (ndev == 0) { set_error("no CUDA device available; libtempest_b200 has no CPU fallback"); return TSDR_ERR_CUDA; }
     TSDR_REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
     TSDR_REQUIRE(max_samples >= 2, "max_samples too small");
+    TSDR_DEVICE(device);
     tsdr_chain* c = new (std::nothrow) tsdr_chain();
     if (!c) return TSDR_ERR_NOMEM;
     memset(c, 0, sizeof(*c));
@@ -967,7 +1025,7 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
     c->ev_pool = new std::vector<cudaEvent_t>();
     c->ev_marks = new std::vector<cudaEvent_t>();
     int rc = TSDR_OK;
-    cudaError_t e = cudaSetDevice(device);
+    cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) {
         if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
         else { e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
@@ -1013,7 +1071,7 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
 
 int tsdr_chain_configure(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     TSDR_REQUIRE(c, "chain is NULL");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     TSDR_CUDA(cudaStreamSynchronize(c->stream));
     return chain_setup(c, Fs, x_t, y_t, fv);
@@ -1027,7 +1085,7 @@ int tsdr_chain_set_alpha(tsdr_chain* c, float alpha) {
 
 int tsdr_chain_reset(tsdr_chain* c) {
     TSDR_REQUIRE(c, "chain is NULL");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     TSDR_CUDA(cudaMemsetAsync(c->d_acc, 0, (size_t)kRenderN * 4, c->stream));
     TSDR_CUDA(cudaMemsetAsync(c->d_best, 0, (size_t)(c->max_frames + 1) * 2 * 8, c->stream));
@@ -1061,7 +1119,7 @@ static int chain_stage(tsdr_chain* c, const void* iq_host, size_t n, float** sta
 int tsdr_chain_push_host(tsdr_chain* c, const float* iq_host, size_t n, int* n_frames) {
     TSDR_REQUIRE(c && (iq_host || n == 0), "NULL argument");
     TSDR_REQUIRE(n <= c->max_samples, "buffer of %zu samples exceeds max_samples %zu", n, c->max_samples);
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     float* staged = nullptr;
     int rc = chain_stage(c, iq_host, n, &staged);
     if (rc) return rc;
@@ -1074,7 +1132,7 @@ int tsdr_chain_push_host(tsdr_chain* c, const float* iq_host, size_t n, int* n_f
 int tsdr_chain_push_host_i16(tsdr_chain* c, const int16_t* iq_host, size_t n, int* n_frames) {
     TSDR_REQUIRE(c && (iq_host || n == 0), "NULL argument");
     TSDR_REQUIRE(n <= c->max_samples, "buffer of %zu samples exceeds max_samples %zu", n, c->max_samples);
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     // the Float32 staging buffers are 16-byte aligned and twice as large as the Int16 samples need, so
     // k_render<true> may read whole 4-sample groups past the copied bytes (stale samples it never uses)
     float* staged = nullptr;
@@ -1089,7 +1147,7 @@ int tsdr_chain_push_host_i16(tsdr_chain* c, const int16_t* iq_host, size_t n, in
 int tsdr_chain_push_device_i16(tsdr_chain* c, const int16_t* iq_dev, size_t n, int* n_frames) {
     TSDR_REQUIRE(c && (iq_dev || n == 0), "NULL argument");
     TSDR_REQUIRE((reinterpret_cast<uintptr_t>(iq_dev) & 15) == 0, "Int16 device buffer must be 16-byte aligned");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     return chain_run(c, reinterpret_cast<const float*>(iq_dev), n, n_frames, false, nullptr, true);
 }
 
@@ -1097,7 +1155,7 @@ namespace tsdr {
 static int chain_push_deliver(tsdr_chain* c, const void* iq_host, size_t n, int* n_frames, float* image_out_host, bool i16) {
     TSDR_REQUIRE(c && (iq_host || n == 0) && image_out_host, "NULL argument");
     TSDR_REQUIRE(n <= c->max_samples, "buffer of %zu samples exceeds max_samples %zu", n, c->max_samples);
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     float* staged = nullptr;
     int rc = chain_stage(c, iq_host, n, &staged, i16 ? 4 : 8);
     if (rc) return rc;
@@ -1150,7 +1208,7 @@ int tsdr_chain_push_ring(tsdr_chain* c, tsdr_ring* r, int sample_format, int tim
 
 int tsdr_chain_wait_delivery(tsdr_chain* c, int age) {
     TSDR_REQUIRE(c && (age == 0 || age == 1), "age must be 0 (latest delivery) or 1 (the one before)");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     TSDR_CUDA(cudaEventSynchronize(c->ev_out[(c->out_parity ^ 1 ^ age) & 1]));
     return TSDR_OK;
 }
@@ -1159,7 +1217,7 @@ int tsdr_chain_prime_host(tsdr_chain* c, const float* iq_host, size_t n) {
     TSDR_REQUIRE(c && iq_host, "NULL argument");
     TSDR_REQUIRE(n <= c->max_samples, "buffer of %zu samples exceeds max_samples %zu", n, c->max_samples);
     TSDR_REQUIRE(!(c->flags & TSDR_CHAIN_NO_ALIGN), "priming is meaningless without frame alignment");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     float* staged = nullptr;
     int rc = chain_stage(c, iq_host, n, &staged);
     if (rc) return rc;
@@ -1173,20 +1231,20 @@ int tsdr_chain_prime_device(tsdr_chain* c, const float* iq_dev, size_t n) {
     TSDR_REQUIRE(c && iq_dev, "NULL argument");
     TSDR_REQUIRE((reinterpret_cast<uintptr_t>(iq_dev) & 7) == 0, "device buffer must be 8-byte aligned");
     TSDR_REQUIRE(!(c->flags & TSDR_CHAIN_NO_ALIGN), "priming is meaningless without frame alignment");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     return chain_run(c, iq_dev, n, nullptr, true);
 }
 
 int tsdr_chain_push_device(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames) {
     TSDR_REQUIRE(c && (iq_dev || n == 0), "NULL argument");
     TSDR_REQUIRE((reinterpret_cast<uintptr_t>(iq_dev) & 7) == 0, "device buffer must be 8-byte aligned");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     return chain_run(c, iq_dev, n, n_frames);
 }
 
 int tsdr_chain_sync(tsdr_chain* c) {
     TSDR_REQUIRE(c, "chain is NULL");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     TSDR_CUDA(cudaStreamSynchronize(c->stream));
     return TSDR_OK;
@@ -1194,13 +1252,13 @@ int tsdr_chain_sync(tsdr_chain* c) {
 
 int tsdr_chain_flush(tsdr_chain* c) {
     TSDR_REQUIRE(c, "chain is NULL");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     return chain_join(c);
 }
 
 int tsdr_chain_read_image(tsdr_chain* c, float* out_colmajor) {
     TSDR_REQUIRE(c && out_colmajor, "NULL argument");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     dim3 tg((kRenderW + 31) / 32, (kRenderH + 31) / 32), tb(32, 8);
     k_transpose<<<tg, tb, 0, c->stream>>>(c->d_acc, c->d_tmp, kRenderH, kRenderW);
@@ -1213,7 +1271,7 @@ int tsdr_chain_read_image(tsdr_chain* c, float* out_colmajor) {
 
 int tsdr_chain_read_offsets(tsdr_chain* c, int* s_y, int* s_x, int max, int* n_frames) {
     TSDR_REQUIRE(c, "chain is NULL");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     int n = c->last_frames < max ? c->last_frames : max;
     if (n_frames) *n_frames = c->last_frames;
@@ -1230,7 +1288,7 @@ int tsdr_chain_read_offsets(tsdr_chain* c, int* s_y, int* s_x, int max, int* n_f
 int tsdr_chain_read_scores(tsdr_chain* c, float* beta_x_max, float* beta_y_max, float* sigma_x, float* sigma_y, int max, int* n_frames) {
     TSDR_REQUIRE(c, "chain is NULL");
     TSDR_REQUIRE(!(c->flags & TSDR_CHAIN_NO_ALIGN), "no sync search ran (TSDR_CHAIN_NO_ALIGN)");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     const int n = c->last_frames < max ? c->last_frames : max;
     if (n_frames) *n_frames = c->last_frames;
@@ -1247,7 +1305,7 @@ int tsdr_chain_read_scores(tsdr_chain* c, float* beta_x_max, float* beta_y_max, 
 int tsdr_chain_read_published(tsdr_chain* c, float* out, int max_frames, int* n_frames) {
     TSDR_REQUIRE(c && out, "NULL argument");
     TSDR_REQUIRE(c->flags & TSDR_CHAIN_PUBLISH_ALL, "chain was not created with TSDR_CHAIN_PUBLISH_ALL");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     const int n = c->last_frames < max_frames ? c->last_frames : max_frames;
     if (n_frames) *n_frames = c->last_frames;
@@ -1264,7 +1322,7 @@ int tsdr_chain_read_published(tsdr_chain* c, float* out, int max_frames, int* n_
 
 int tsdr_chain_accumulator(tsdr_chain* c, void** dev_ptr, size_t* n_floats) {
     TSDR_REQUIRE(c, "chain is NULL");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }  // later work on the primary stream sees the finished accumulator
     if (dev_ptr) *dev_ptr = c->d_acc;
     if (n_floats) *n_floats = (size_t)kRenderN;
@@ -1280,7 +1338,7 @@ __global__ void __launch_bounds__(kEwThreads) k_scale(float* a, int n, float f) 
 
 int tsdr_chain_scale_accumulator(tsdr_chain* c, float factor) {
     TSDR_REQUIRE(c, "chain is NULL");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     tsdr::k_scale<<<ew_blocks(kRenderN), kEwThreads, 0, c->stream>>>(c->d_acc, kRenderN, factor);
     c->launches += 1;
@@ -1302,7 +1360,7 @@ int tsdr_chain_launch_count(tsdr_chain* c, uint64_t* count) {
 
 int tsdr_chain_set_profiling(tsdr_chain* c, int enable) {
     TSDR_REQUIRE(c, "chain is NULL");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     c->profiling = enable != 0;
     return TSDR_OK;
@@ -1310,7 +1368,7 @@ int tsdr_chain_set_profiling(tsdr_chain* c, int enable) {
 
 int tsdr_chain_kernel_times(tsdr_chain* c, float ms[TSDR_CHAIN_STAGES], uint64_t pushes[1]) {
     TSDR_REQUIRE(c && ms && pushes, "NULL argument");
-    TSDR_CUDA(cudaSetDevice(c->device));
+    TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
     TSDR_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < TSDR_CHAIN_STAGES; ++i) ms[i] = 0.f;
@@ -1330,7 +1388,7 @@ int tsdr_chain_kernel_times(tsdr_chain* c, float ms[TSDR_CHAIN_STAGES], uint64_t
 
 int tsdr_chain_destroy(tsdr_chain* c) {
     if (!c) return TSDR_OK;
-    cudaSetDevice(c->device);
+    TSDR_DEVICE(c->device);
     if (c->aux) cudaStreamSynchronize(c->aux);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; ++i) { if (c->ev_render[i]) cudaEventDestroy(c->ev_render[i]); if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]); }

@@ -549,7 +549,7 @@ extern "C" {
 
 int tsdr_autocorr_plan_destroy(tsdr_autocorr_plan* p) {
     if (!p) return TSDR_OK;
-    cudaSetDevice(p->device);
+    TSDR_DEVICE(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     cudaFree(p->d_tables); cudaFree(p->d_T); cudaFree(p->d_U); cudaFree(p->d_lin);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
@@ -599,7 +599,8 @@ int tsdr_autocorr_plan_create(tsdr_autocorr_plan** out, int device, size_t n, vo
     for (int i = 0; i < B; ++i) { revB[i] = dif_frequency(i, B, fp.radB); posB[revB[i]] = i; }
 
     int rc = TSDR_OK;
-    e = cudaSetDevice(device);
+    DeviceScope scope;
+    if ((rc = scope.enter(device))) { delete p; return rc; }
     if (e == cudaSuccess) {
         if (stream) { p->stream = (cudaStream_t)stream; p->own_stream = false; }
         else { e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking); p->own_stream = true; }
@@ -624,9 +625,9 @@ int tsdr_autocorr_plan_create(tsdr_autocorr_plan** out, int device, size_t n, vo
     fp.T = p->d_T; fp.U = p->d_U;
     p->smem_cols = (size_t)col_padded(A * C) * sizeof(float2);
     p->smem_mid = (size_t)2 * row_padded(B) * sizeof(float2);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cols);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ifft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cols);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fft_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_mid);
+    if (e == cudaSuccess) e = allow_max_dynamic_smem(k_fft_cols);
+    if (e == cudaSuccess) e = allow_max_dynamic_smem(k_ifft_cols);
+    if (e == cudaSuccess) e = allow_max_dynamic_smem(k_fft_mid);
     {
         int loga = 0, logb = 0;
         while ((1 << loga) < A) ++loga;
@@ -636,19 +637,19 @@ int tsdr_autocorr_plan_create(tsdr_autocorr_plan** out, int device, size_t n, vo
         // TSDR_FFT_TWO_LEVEL=1 (read once, here) keeps a plan on the two-level kernels: tools/fft_variants.py times both
         p->has_fft3 = !getenv("TSDR_FFT_TWO_LEVEL") && find_fft3(logN, logb, &p->f3);
         if (p->has_fft3 && e == cudaSuccess) {
-            e = cudaFuncSetAttribute(p->f3.p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p1);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p1_padded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p1);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p1);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p2);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p2);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->f3.p3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->f3.smem_p3);
+            e = allow_max_dynamic_smem(p->f3.p1);
+            if (e == cudaSuccess) e = allow_max_dynamic_smem(p->f3.p1_padded);
+            if (e == cudaSuccess) e = allow_max_dynamic_smem(p->f3.p5);
+            if (e == cudaSuccess) e = allow_max_dynamic_smem(p->f3.p2);
+            if (e == cudaSuccess) e = allow_max_dynamic_smem(p->f3.p4);
+            if (e == cudaSuccess) e = allow_max_dynamic_smem(p->f3.p3);
         }
         p->has_fast = find_fast(loga, logb, &p->fast);
         if (p->has_fast && e == cudaSuccess) {
-            e = cudaFuncSetAttribute(p->fast.cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast.smem_cols);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->fast.cols_padded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast.smem_cols);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->fast.icols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast.smem_cols);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(p->fast.mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fast.smem_mid);
+            e = allow_max_dynamic_smem(p->fast.cols);
+            if (e == cudaSuccess) e = allow_max_dynamic_smem(p->fast.cols_padded);
+            if (e == cudaSuccess) e = allow_max_dynamic_smem(p->fast.icols);
+            if (e == cudaSuccess) e = allow_max_dynamic_smem(p->fast.mid);
         }
     }
     if (e != cudaSuccess) rc = cuda_fail(e, "tsdr_autocorr_plan_create", __FILE__, __LINE__);
@@ -663,7 +664,7 @@ int tsdr_autocorr_plan_exec(tsdr_autocorr_plan* p, const float* x_dev, size_t in
     TSDR_REQUIRE(index_min >= 1 && index_max >= index_min, "need 1 <= indexMin <= indexMax");
     if (index_max > p->n) { set_error("BoundsError: indexMax %zu beyond the %zu-point correlation", index_max, p->n); return TSDR_ERR_BOUNDS; }
     TSDR_REQUIRE((reinterpret_cast<uintptr_t>(x_dev) & 7) == 0, "input must be 8-byte aligned");
-    TSDR_CUDA(cudaSetDevice(p->device));
+    TSDR_DEVICE(p->device);
     FftParams fp = p->fp;
     fp.x = x_dev; fp.n_valid = (int64_t)p->n; fp.log_scale = log_scale;
     if (p->fold) { fp.out = p->d_lin; fp.m_lo = 0; fp.m_hi = (int64_t)p->n; fp.raw = 1; }
@@ -746,7 +747,8 @@ extern "C" {
 
 int tsdr_upsampler_destroy(tsdr_upsampler* u) {
     if (!u) return TSDR_OK;
-    if (u->plan) { cudaSetDevice(u->plan->device); cudaStreamSynchronize(u->plan->stream); }
+    DeviceScope scope;
+    if (u->plan) { scope.enter(u->plan->device); cudaStreamSynchronize(u->plan->stream); }
     cudaFree(u->d_H); cudaFree(u->d_in); cudaFree(u->d_out);
     tsdr_autocorr_plan_destroy(u->plan);
     delete u->H;
@@ -764,7 +766,7 @@ int tsdr_upsampler_create(size_t buffer_size, int up_coeff, tsdr_upsampler** out
                   "only handles those lengths", M);
         return TSDR_ERR_UNSUPPORTED;
     }
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     tsdr_upsampler* u = new (std::nothrow) tsdr_upsampler();
     if (!u) return TSDR_ERR_NOMEM;
     memset(u, 0, sizeof(*u));
@@ -811,7 +813,7 @@ int tsdr_upsampler_apply_f32(tsdr_upsampler* u, float* out, size_t n_out, const 
     TSDR_REQUIRE(n_in == u->n_in, "Size of input %zu should match size used during init %zu", n_in, u->n_in);
     TSDR_REQUIRE(n_out >= u->M, "output holds %zu samples, need bufferSize*upCoeff = %zu", n_out, u->M);
     tsdr_autocorr_plan* p = u->plan;
-    TSDR_CUDA(cudaSetDevice(p->device));
+    TSDR_DEVICE(p->device);
     cudaStream_t st = p->stream;
     TSDR_CUDA(cudaMemcpyAsync(u->d_in, in, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
     FftParams fp = p->fp;
@@ -849,7 +851,7 @@ int tsdr_autocorr_f32(const float* x, size_t len, double Fs, double min_delay, d
     const int64_t index_min = 1 + round_even(min_delay * Fs), index_max = round_even(max_delay * Fs);
     size_t n = (size_t)(2 * index_max);
     if (len < n) n = len;
-    if ((rc = ensure_device())) return rc;
+    TSDR_TIER1_DEVICE();
     tsdr_autocorr_plan* plan = nullptr;
     if ((rc = tsdr_autocorr_plan_create(&plan, current_device(), n, nullptr))) return rc;
     void *d_x = nullptr, *d_out = nullptr;
@@ -876,7 +878,7 @@ int tsdr_get_spectrum_f32(const float* sig_iq, size_t N, int log_scale, float* y
     TSDR_REQUIRE((sig_iq && y) || N == 0, "NULL argument");
     if (N == 0) return TSDR_OK;
     TSDR_REQUIRE(N <= ((size_t)1 << 23), "getSpectrum: at most 2^23 samples");
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     const bool direct = is_pow2(N) && N >= 32;
     size_t M = N;
     if (!direct) { M = 32; while (M < 2 * N - 1) M <<= 1; }
@@ -933,7 +935,7 @@ static int spec_segments(const float* sig_iq, size_t len, int size_fft, int mode
                  "sizeFFT must be a power of two in [2, 8192] (got %d)", size_fft);
     const int64_t nseg = (int64_t)(len / (size_t)size_fft);
     TSDR_REQUIRE((sig_iq && out) || nseg == 0, "NULL argument");
-    int rc = ensure_device(); if (rc) return rc;
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     SpecParams sp;
     sp.len = size_fft; sp.rad = make_radices(size_fft); sp.nseg = nseg; sp.mode = mode;
     sp.rows = std::max(1, 8192 / size_fft);
@@ -959,7 +961,7 @@ static int spec_segments(const float* sig_iq, size_t len, int size_fft, int mode
     if (e == cudaSuccess && n_used) e = cudaMemcpy(d_x, sig_iq, n_used * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_tab, tw.data(), size_fft * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy((char*)d_tab + size_fft * sizeof(float2), pos.data(), size_fft * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spec_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = allow_max_dynamic_smem(k_spec_batch);
     if (e == cudaSuccess) {
         sp.x = (const float2*)d_x; sp.tw = (const float2*)d_tab; sp.pos = (const int*)((char*)d_tab + size_fft * sizeof(float2));
         sp.out = (float*)d_out; sp.partial = (float*)d_part;

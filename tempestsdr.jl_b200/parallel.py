@@ -1,4 +1,7 @@
-"""Multi-GPU host logic: one process per GPU, torch.distributed for the plumbing.
+"""Multi-GPU host logic: one process per GPU.  On GPUs the combine runs behind the C ABI (tsdr_comm_* /
+tsdr_chain_allreduce: NCCL bound by the library itself, the EMA tail weight folded into the collective);
+torch.distributed only launches the ranks and carries the 128-byte communicator id.  The gloo path below
+(allreduce_partial on CPU tensors) exists for the CPU tests of the host logic.
 
 The chain shards without any data-path exchange:
   * independent recv! buffers          -> buffer b on rank b mod N          (cfg 3)
@@ -61,21 +64,21 @@ def allreduce_partial(acc, alpha, frames_after, group=None, sum_mode=False, tota
     return acc
 
 
-def integrate_frames_sharded(make_chain, frame_source, n_frames, alpha, rank, world, group=None):
+def integrate_frames_sharded(make_chain, frame_source, n_frames, alpha, rank, world, comm=None):
     """cfg 5: integrate `n_frames` frames over `world` GPUs.
     make_chain(): a fresh tempestsdr_b200.Chain (zero accumulator) on this rank's GPU, sized for one block.
     frame_source(k0, k1): complex64 samples of frames k0..k1-1 (host array).
-    Returns the combined image as a torch tensor (scan order 600x800) present on every rank."""
-    import torch
+    comm: this rank's tempestsdr_b200.Comm (the C-ABI NCCL communicator); None for a single rank.
+    Returns (combined image as numpy (600, 800), chain); the image is present on every rank."""
     k0, k1 = shard_contiguous(n_frames, world, rank)
     ch = make_chain()
     if k0 > 0:
         ch.prime(frame_source(k0 - 1, k0))  # halo frame: gives this block the sequential run's first s_y
     if k1 > k0:
         ch.push(frame_source(k0, k1))
-    ch.flush()
-    acc = accumulator_tensor(ch)
-    with torch.cuda.stream(torch.cuda.ExternalStream(ch.stream())):
-        out = allreduce_partial(acc, alpha, n_frames - k1, group=group).clone()
-    torch.cuda.synchronize()
-    return out.view(600, 800), ch
+    weight = ema_tail_weight(alpha, n_frames - k1)
+    if comm is not None and world > 1:
+        comm.allreduce_chain(ch, weight)
+    elif weight != 1.0:
+        ch.scale_accumulator(weight)
+    return ch.image(), ch

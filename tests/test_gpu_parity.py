@@ -461,16 +461,20 @@ def _nccl_worker(rank, world, port, iq, Fs, mode, alpha, N, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    # torch.distributed (gloo) only carries the 128-byte communicator id; the all-reduce itself is the library's own
+    # NCCL communicator behind the C ABI (tsdr_comm_init_rank / tsdr_chain_allreduce)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = tsdr.Comm.from_torch_distributed(rank)
     x_t, y_t, fv = mode
     S = orc.frame_samples(Fs, fv)
     k0, k1 = parallel.shard_contiguous(N, world, rank)
     img, ch = parallel.integrate_frames_sharded(
         lambda: tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=alpha, max_samples=(k1 - k0) * S, device=rank),
-        lambda a, b: iq[a * S:b * S], N, alpha, rank, world)
-    if rank == 0:
-        np.save(out_path, img.cpu().numpy())
+        lambda a, b: iq[a * S:b * S], N, alpha, rank, world, comm=comm)
+    assert comm.collectives() == 1
+    np.save(out_path + ".%d.npy" % rank, img)
     ch.close()
+    comm.close()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -490,7 +494,9 @@ def test_two_gpu_nccl_allreduce_of_partial_frames(synth, tmp_path):
         port = s.getsockname()[1]
     out = str(tmp_path / "img.npy")
     mp.spawn(_nccl_worker, args=(2, port, iq, Fs, mode, alpha, N, out), nprocs=2, join=True)
-    np.testing.assert_allclose(np.load(out), ref, rtol=2e-6, atol=1e-7)
+    r0, r1 = np.load(out + ".0.npy"), np.load(out + ".1.npy")
+    assert np.array_equal(r0, r1)   # every rank holds the same combined image
+    np.testing.assert_allclose(r0, ref, rtol=2e-6, atol=1e-7)
 
 
 def test_gpu_matches_committed_goldens():
