@@ -6,7 +6,10 @@ One object per .cu (the exact-rounding files with -fmad=false, the FFT with
 fused multiply-adds), linked into tempestsdr.jl_b200/libtempest_b200.so.  The
 .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
+import hashlib
+import json
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -34,15 +37,85 @@ def nvcc():
     raise RuntimeError("nvcc not found")
 
 
+HASHFILE = os.path.join(HERE, "libtempest_b200.srchash")   # beside the .so: git-ignored, travels with gpurun
+PROFILES = os.path.join(HERE, "..", "profiles")
+
+
 def _deps():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "tempest_b200.h")]
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "tempest_b200.h")]
+
+
+def source_hash():
+    """sha256 over every source the library is built from and the flags it is built with"""
+    h = hashlib.sha256()
+    for p in _deps():
+        h.update(os.path.basename(p).encode() + b"\0")
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(repr((ARCH, COMMON, UNITS)).encode())
+    return h.hexdigest()
 
 
 def stale():
-    if not os.path.exists(SO):
+    """the binary is current iff the hash recorded beside it equals the hash of the sources: file times do not
+    survive a checkout or the copy to the GPU box, and a stale .so must never be reused silently"""
+    if not os.path.exists(SO) or not os.path.exists(HASHFILE):
         return True
-    t = os.path.getmtime(SO)
-    return any(os.path.getmtime(p) > t for p in _deps() + [os.path.abspath(__file__)])
+    with open(HASHFILE) as f:
+        return f.read().strip() != source_hash()
+
+
+MNEMONICS = ["UBLKCP", "SYNCS", "DADD.RM", "DADD", "DMUL", "DFMA", "MUFU.RSQ", "MUFU.RCP", "MUFU.LG2", "F2F", "FFMA", "FADD", "FMUL",
+             "SHFL", "LDS", "STS", "LDG", "STG", "ATOMG", "RED", "BAR", "HMMA", "UTCHMMA", "UTMALDG"]
+
+
+def sass_summary(so=SO, write=True):
+    """per kernel: instruction count, the mnemonics DESIGN.md cites (UBLKCP = TMA bulk copy, SYNCS = mbarrier,
+    DADD.RM = the round-down floor trick, MUFU.* ...) and a sha256 of the instruction stream, from cuobjdump -sass.
+    Tracked evidence under profiles/ (sass_summary.txt / .json); bench.py ties ncu traffic captures to these hashes."""
+    cuobjdump = os.path.join(os.path.dirname(nvcc()), "cuobjdump")
+    r = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("cuobjdump failed: " + r.stderr)
+    funcs, cur = {}, None
+    for line in r.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
+        if m and cur is not None:
+            funcs[cur].append(re.sub(r"\s+", " ", m.group(1).strip()))
+    filt = shutil.which("cu++filt") or os.path.join(os.path.dirname(nvcc()), "cu++filt")
+    names = list(funcs)
+    try:
+        dem = subprocess.run([filt] + names, capture_output=True, text=True).stdout.splitlines()
+        dem = [d.replace("tsdr::", "") for d in dem]
+        dem = [re.sub(r"\((?:[^()]|\([^()]*\))*\)$", "", d) for d in dem]
+        dem = [re.sub(r"^void ", "", d) for d in dem]
+    except Exception:
+        dem = names
+    if len(dem) != len(names):
+        dem = names
+    out = {}
+    for nm, d in zip(names, dem):
+        ins = funcs[nm]
+        ops = [i.split(" ", 2)[1] if i.startswith("@") and " " in i else i.split(" ", 1)[0] for i in ins]
+        counts = {k: sum(1 for o in ops if o == k or o.startswith(k + ".")) for k in MNEMONICS}
+        counts["DADD.RM"] = sum(1 for o in ops if o.startswith("DADD") and ".RM" in o)
+        out[d] = {"instructions": len(ins), "sha256": hashlib.sha256("\n".join(ins).encode()).hexdigest()[:16],
+                  "mnemonics": {k: v for k, v in counts.items() if v}}
+    if write and os.path.isdir(PROFILES):
+        with open(os.path.join(PROFILES, "sass_summary.json"), "w") as f:
+            json.dump(out, f, indent=1, sort_keys=True)
+        with open(os.path.join(PROFILES, "sass_summary.txt"), "w") as f:
+            f.write("# cuobjdump -sass of libtempest_b200.so (sm_100a), written by tempestsdr.jl_b200/build.py at every build\n")
+            f.write("# kernel | SASS instructions | sha256[:16] of the instruction stream | mnemonic counts\n")
+            for d in sorted(out):
+                f.write("%s | %d | %s | %s\n" % (d, out[d]["instructions"], out[d]["sha256"],
+                                               " ".join("%s=%d" % kv for kv in sorted(out[d]["mnemonics"].items()))))
+    return out
 
 
 def build(force=False, verbose=False):
@@ -68,8 +141,14 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + log[-1])
     os.replace(SO + ".tmp", SO)
+    with open(HASHFILE, "w") as f:
+        f.write(source_hash() + "\n")
     with open(os.path.join(OBJDIR, "build.log"), "w") as f:
         f.write("\n".join(log))
+    try:
+        sass_summary()
+    except Exception as exc:   # evidence, not a build product
+        log.append("sass summary skipped: %r" % (exc,))
     if verbose:
         print("\n".join(log))
     return SO

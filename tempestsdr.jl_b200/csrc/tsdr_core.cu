@@ -1050,8 +1050,8 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_staging_free[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaMalloc(&c->d_iq2[i], (max_samples + 2) * 8);
-        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_iq2[i], 0, (max_samples + 2) * 8, c->stream);
+        // the staging buffers themselves are allocated by the first host push (chain_stage): a chain that is only
+        // fed device buffers never pays 2 x max_samples x 8 bytes of HBM for them
     }
     if (e == cudaSuccess) e = cudaMalloc(&c->d_acc, (size_t)kRenderN * 4);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tmp, (size_t)kRenderN * 4);
@@ -1105,6 +1105,10 @@ static int chain_stage(tsdr_chain* c, const void* iq_host, size_t n, float** sta
     c->stage_parity ^= 1;
     // only the samples of complete frames are used (GUI.jl:137,165-166)
     const size_t used = (n / (size_t)c->S) * (size_t)c->S;
+    if (!c->d_iq2[sp]) {
+        TSDR_CUDA(cudaMalloc(&c->d_iq2[sp], (c->max_samples + 2) * 8));
+        TSDR_CUDA(cudaMemsetAsync(c->d_iq2[sp], 0, (c->max_samples + 2) * 8, c->copy));
+    }
     if (used) {
         TSDR_CUDA(cudaStreamWaitEvent(c->copy, c->ev_staging_free[sp], 0));  // render of the push before last has read it
         TSDR_CUDA(cudaMemcpyAsync(c->d_iq2[sp], iq_host, used * sample_bytes, cudaMemcpyHostToDevice, c->copy));

@@ -152,6 +152,7 @@ CHAIN_CASES = [
     (2.0e6, (800, 525, 60.0), 4, 0.1),      # upsampling in 1-D, y_t < 600 (clamped 2-D)
     (2.0e6, (1056, 628, 60.0), 3, 0.3),     # typical
     (20.0e6, (2576, 1125, 60.0), 2, 0.1),   # BASELINE cfg 2 shape
+    (200.0e6, (2720, 1481, 60.0), 2, 0.1),  # BASELINE cfg 3 shape: the 200 MS/s north-star stream (S = 3 333 333, odd)
     (8.0e6, (800, 600, 70.0), 3, 0.25),     # (600, 800): downgradeImage copies
     (30.0e6, (832, 445, 85.0), 2, 0.0),     # 1-D downsampling (S > P), alpha = 0
     (480000.0 * 50, (800, 600, 50.0), 2, 0.5),  # S == P: both resizes copy
@@ -213,6 +214,27 @@ def test_chain_int16_push_matches_widened_float_push(synth):
     with pytest.raises(tsdr.TempestError):
         d.push_device_i16(dev.data_ptr() + 4, n - 1)   # not 16-byte aligned
     a.close(); b.close(); d.close()
+
+
+def test_chain_int16_cfg3_shape(synth):
+    # the north-star shape fed as `:short` samples: k_render<Int16> against the oracle on the widened buffer
+    Fs, x_t, y_t, fv, frames = 200.0e6, 2720, 1481, 60.0, 2
+    S = orc.frame_samples(Fs, fv)
+    assert S == 3333333
+    n = S * frames + 3
+    iq = synth.make_iq(n, Fs, x_t, y_t, fv, seed=91)
+    i16 = np.empty((n, 2), np.int16)
+    i16[:, 0] = np.clip(np.rint(iq.real * 2048.0), -32768, 32767)
+    i16[:, 1] = np.clip(np.rint(iq.imag * 2048.0), -32768, 32767)
+    wide = (i16[:, 0].astype(np.float32) + 1j * i16[:, 1].astype(np.float32)).astype(np.complex64)
+    ref, _, sy_ref, sx_ref = orc.chain_buffer(wide, Fs, x_t, y_t, fv, 0.1, orc.SyncXY(), np.zeros((600, 800), np.float32),
+                                              publish=False, nthreads=2)
+    ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=0.1, max_samples=n)
+    assert ch.push_i16(i16) == frames
+    sy, sx = ch.offsets()
+    assert np.array_equal(sy, sy_ref) and np.array_equal(sx, sx_ref)
+    assert np.array_equal(ch.image(), ref)
+    ch.close()
 
 
 def _carrier_signal(n, seed):
@@ -382,6 +404,23 @@ def test_autocorr_matches_oracle(n, Fs, maxDelay):
     lin_ref, _ = orc.calculate_autocorrelation(x, Fs, 0, maxDelay, scale="lin")
     lin, _ = tsdr.calculate_autocorrelation(x, Fs, 0, maxDelay, scale="lin")
     np.testing.assert_allclose(lin, lin_ref, rtol=2e-4)
+
+
+@pytest.mark.parametrize("log2n", [24, 26])
+def test_autocorr_metric_sizes_match_oracle(log2n):
+    # the sizes the M2 metric is quoted on (BASELINE.json: ms per 2^24 samples; cfg 4 buffers of 2^26), three-level kernels,
+    # against the oracle's own Float32 FFT: same tolerance as the small cases, argmax of the lag slice equal
+    n = 1 << log2n
+    x = _periodic_power(n, 33333, log2n)   # a "frame" period that does not divide n: the peak sits on a non-trivial lag
+    ref, lags_ref = orc.calculate_autocorrelation(x, float(n), 0, 0.5)
+    got, lags = tsdr.calculate_autocorrelation(x, float(n), 0, 0.5)
+    assert got.shape == ref.shape == (n // 2,) and np.array_equal(lags, lags_ref)
+    near = ref > ref.max() - 60.0
+    assert np.max(np.abs(got[near] - ref[near])) <= 1e-2
+    assert orc.findmax(got[1:])[1] == orc.findmax(ref[1:])[1]
+    # the windowed picks extract_configuration makes (src/GUI.jl:74-81) land on the same lag too
+    for lo, hi in ((30000, 40000), (n // 8, n // 4)):
+        assert orc.findmax(got[lo:hi])[1] == orc.findmax(ref[lo:hi])[1]
 
 
 def test_autocorr_min_delay_and_bounds():
