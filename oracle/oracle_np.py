@@ -161,14 +161,24 @@ def filt5(h, x):
     return acc.astype(np.float32)
 
 
+def base_sum(c):
+    """Base.sum(::Vector{Float32}): pairwise halving down to runs of fewer than 1025 elements (reduce.jl,
+    mapreduce_impl, blksize 1024); each run fixed to a 32-lane SIMD-shaped order (see tsdr_oracle.c:orc_sum_base)"""
+    c = np.asarray(c, np.float32)
+    if c.size - 1 < 1024:
+        lanes = [seq_sum(c[l::32]) for l in range(min(32, c.size))]
+        tot = lanes[0]
+        for v in lanes[1:]:
+            tot = np.float32(tot + v)
+        return tot
+    mid = (c.size - 1) >> 1          # imid = ifirst + (ilast - ifirst) >> 1, 0-based inclusive
+    return np.float32(base_sum(c[: mid + 1]) + base_sum(c[mid + 1:]))
+
+
 def fill_beta(c, wmin, wmax):  # src/FrameSynchronisation.jl:94-112 -> (nw, n)
     c = np.asarray(c, np.float32)
     n = c.size
-    # Sigma = sum(c): fixed to a 32-lane SIMD-shaped order (see tsdr_oracle.c:orc_fill_beta)
-    lanes = [seq_sum(c[l::32]) for l in range(min(32, n))]
-    Sigma = lanes[0]
-    for v in lanes[1:]:
-        Sigma = np.float32(Sigma + v)
+    Sigma = base_sum(c)
     ctr = np.arange(n)  # 0-based centres
     acc = np.zeros(n, np.float32)
     for k in range(-(wmin - 1), wmin):

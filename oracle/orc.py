@@ -350,6 +350,29 @@ def chain_buffer(iq, Fs, x_t, y_t, fv, alpha, sync, image_out, publish=True, nth
     return _from_cm(acc, RENDER_H, RENDER_W), fr, sy[:nb], sx[:nb]
 
 
+def investigate_capture(sigRx, Fs, find_closest_configuration, offset=420_000, N=500):
+    """the headless recipe of production/investigate_data.jl:37-97,159-206 with the oracle's functions (checker for
+    BASELINE configs[0]); find_closest_configuration is the host-side table lookup (src/VideoConfigurations.jl:117-124)"""
+    sigId = amDemod(sigRx)
+    G, _ = calculate_autocorrelation(sigId, Fs, 0, 1 / 10)
+    rates, Gl = zoom_autocorr(G, Fs, 50, 90)
+    posMax = findmax(Gl)[1]
+    fv = float(np.round(1 / (1 / rates[posMax - 1]), 2))
+    _, Gs = zoom_autocorr(G, Fs, fv, fv + 0.3)
+    m = findmax(Gs[:N])[1]
+    y_t = 1 / (fv * (m / Fs))
+    found = find_closest_configuration(y_t, fv)
+    name = list(found)[0]
+    w, h = found[name].width, found[name].height
+    d = frame_samples(Fs, fv)
+    img = sig_to_image(sigId[offset: offset + d], h, w)
+    so = SyncXY(h, w)
+    tup = vsync(img, so)
+    idx = int(np.floor((tup[1] * w + tup[0]) / (w * h) / fv * Fs))
+    img2 = sig_to_image(sigId[offset + idx: offset + idx + d], h, w)
+    return dict(fv=fv, posMax=posMax, m=m, y_t=y_t, name=name, vsync=tup, idx=idx, image=img, image_synced=img2)
+
+
 def num_threads():
     """threads orc_chain_buffer can use: every core this process may run on when the library has OpenMP
     (launchers such as torchrun export OMP_NUM_THREADS=1, which the explicit nthreads argument overrides)"""

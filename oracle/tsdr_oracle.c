@@ -387,16 +387,31 @@ static inline int orc_mod_index(int k, int n) { /* modIndex :120-122, returns 0-
     return m;
 }
 
-void orc_fill_beta(float* beta, const float* c, int n, int wmin, int wmax) { /* :94-112 */
-    /* Sigma = sum(c_v): Base uses a @simd loop below 1024 elements, whose association is CPU
-     * dependent.  FIXED here to the shape of a 32-lane SIMD reduction: lane l adds elements
-     * l, l+32, l+64, ... in order, then the lane sums are added in lane order. */
-    float Sigma = 0.0f;
+/* Base.sum(::Vector{Float32}) = mapreduce_impl(identity, add_sum, A, 1, n, 1024) (reduce.jl): pairwise halving
+ * (imid = ifirst + (ilast-ifirst)>>1) down to runs with ilast - ifirst < 1024, each run an @simd loop whose
+ * association is CPU dependent.  The run is FIXED here to the shape of a 32-lane SIMD reduction: lane l adds
+ * elements l, l+32, l+64, ... of the run in order, then the lane sums are added in lane order.  For the GUI's
+ * 600 / 800 element projections the whole vector is one run. */
+static float orc_sum_run(const float* c, int lo, int hi) { /* inclusive, 0-based */
+    const int n = hi - lo + 1;
+    float tot = 0.0f;
     for (int l = 0; l < 32 && l < n; ++l) {
-        float part = c[l];
-        for (int i = l + 32; i < n; i += 32) part = part + c[i];
-        Sigma = (l == 0) ? part : Sigma + part;
+        float part = c[lo + l];
+        for (int i = l + 32; i < n; i += 32) part = part + c[lo + i];
+        tot = (l == 0) ? part : tot + part;
     }
+    return tot;
+}
+float orc_sum_base(const float* c, int lo, int hi) {
+    if (hi - lo < 1024) return orc_sum_run(c, lo, hi);
+    const int mid = lo + ((hi - lo) >> 1);
+    const float v1 = orc_sum_base(c, lo, mid);
+    const float v2 = orc_sum_base(c, mid + 1, hi);
+    return v1 + v2;
+}
+
+void orc_fill_beta(float* beta, const float* c, int n, int wmin, int wmax) { /* :94-112 */
+    const float Sigma = orc_sum_base(c, 0, n - 1); /* :96 */
     const int nw = 1 + wmax - wmin;
     for (int ctr = 1; ctr <= n; ++ctr) {
         /* averagePixel(c_v, c, wmin-1, n): accum starts as Int 0 -> first add is exact */

@@ -12,6 +12,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import TempestError, check
+from .dat_files import readComplexBinary, readComplexBinaryRaw, writeComplexBinary  # noqa: F401
 from .video_configurations import (VideoMode, allVideoConfigurations, find_closest_configuration,  # noqa: F401
                                    find_configuration, get_refresh_rates, dict2video)
 
@@ -20,7 +21,7 @@ __all__ = [
     "calculate_autocorrelation", "zoom_autocorr", "getSpectrum", "getWelch", "getWaterfall", "findmax", "findmax_device", "findmax_windows_device", "sweep_refresh_hypotheses", "SyncXY", "vsync", "fullScale",
     "VideoMode", "allVideoConfigurations", "find_closest_configuration", "find_configuration",
     "get_refresh_rates", "dict2video", "getImageDuration", "delay2yt", "yt2index", "yt2delay",
-    "Chain", "Comm", "comm_available", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "search_configuration", "blanking_contrast", "auto_configure", "TempestError", "RENDERING_SIZE",
+    "readComplexBinary", "readComplexBinaryRaw", "writeComplexBinary", "toImage", "investigate_capture", "Chain", "Comm", "comm_available", "AtomicCircularBuffer", "circ_put", "circ_take", "AutocorrPlan", "extract_configuration", "estimate_lines", "search_configuration", "blanking_contrast", "auto_configure", "TempestError", "RENDERING_SIZE",
     "device_count", "set_device",
 ]
 
@@ -761,6 +762,48 @@ def auto_configure(iq, Fs, frames=3, nudge=3, refresh_tol=1.0, delayRate=1 / 10,
     ranking = search_configuration(z, Fs, cands, frames=frames, device=device, rank=rank, world=world)
     best = ranking[0][1] if ranking else VideoMode(entry.width, y0, float(fv))
     return best, float(fv), float(y_hat), name, ranking
+
+
+def toImage(sigId, offset, Fs, finalConfig):
+    """toImage(sigId, offset, Fs, finalConfig) of production/investigate_data.jl:159-169: the frame starting `offset`
+    samples into the (demodulated) capture, as a height x width image -- the same arithmetic as sig_to_image"""
+    d = getImageDuration(finalConfig, Fs)
+    s = np.asarray(sigId)[offset: offset + d]
+    if s.size < d:
+        raise IndexError("BoundsError: frame of %d samples at offset %d exceeds the capture" % (d, offset))
+    return sig_to_image(s, int(finalConfig.height), int(finalConfig.width))
+
+
+def investigate_capture(sigRx, Fs, offset=420_000, rate_min=50, rate_max=90, N=500):
+    """The headless replay recipe of production/investigate_data.jl (BASELINE configs[0]) on the GPU, step by step with
+    the reference's own function names: amDemod (:37), calculate_autocorrelation(sigId, Fs, 0, 1/10) (:52), refresh peak
+    (:55-62, fv rounded to 2 digits), line peak (:69-82), find_closest_configuration (:92), toImage (:194), SyncXY / vsync
+    on the FULL-SIZE frame (:196-197), sample-offset correction (:200-201) and the re-rendered frame (:206).
+    Returns a dict with every intermediate the recipe names."""
+    sigId = amDemod(sigRx)
+    Gamma, _ = calculate_autocorrelation(sigId, Fs, 0, 1 / 10)
+    rates_large, Gamma_large = zoom_autocorr(Gamma, Fs, rate_min=rate_min, rate_max=rate_max)
+    _, posMax = findmax(Gamma_large)
+    posMax_time = 1 / rates_large[posMax - 1]
+    fv = float(np.round(1 / posMax_time, 2))           # round(1/posMax_time; digits=2)
+    _, Gamma_short = zoom_autocorr(Gamma, Fs, rate_min=fv, rate_max=fv + 0.3)
+    m = findmax(Gamma_short[:N])[1]
+    tau = m / Fs
+    y_t = 1 / (fv * tau)
+    found = find_closest_configuration(y_t, fv)
+    name = list(found)[0]                                # first(find_closest_configuration(y_t, fv))
+    est = found[name]
+    finalConfig = VideoMode(est.width, est.height, fv)
+    anImage = toImage(sigId, offset, Fs, finalConfig)
+    sync = SyncXY(anImage)
+    tup = vsync(anImage, sync)
+    sync.close()
+    tau_px = tup[1] * finalConfig.width + tup[0]         # tup[2] * width + tup[1]
+    idx = int(np.floor(tau_px / (finalConfig.width * finalConfig.height) / fv * Fs))
+    d = getImageDuration(finalConfig, Fs)
+    anImage2 = sig_to_image(sigId[offset + idx: offset + idx + d], int(finalConfig.height), int(finalConfig.width))
+    return {"fv": fv, "posMax": int(posMax), "m": int(m), "y_t": float(y_t), "name": name, "config": finalConfig,
+            "vsync": tuple(tup), "idx": idx, "image": anImage, "image_synced": anImage2}
 
 
 def estimate_lines(Gamma, Fs, fv, N=500):

@@ -615,7 +615,23 @@ static int launch_sync_stage(const float* frames, int n_frames, float* c_v, floa
                              cudaStream_t st) {
     (void)c_v; (void)c_h;
     k_project<<<dim3(kBands, n_frames), kProjThreads, kProjSmem, st>>>(frames, sp);
-    k_beta<<<dim3(n_frames, kBetaCtasX + kBetaCtasY), kBetaThreads, 0, st>>>(sp);
+    k_beta<false><<<dim3(n_frames, kBetaCtasX + kBetaCtasY), kBetaThreads, 0, st>>>(sp);
+    return TSDR_OK;
+}
+
+// SyncXY of any other image size: one frame, column-major image in img_cm, its scan-order copy in img
+static size_t beta_generic_smem(const SyncParams& sp) {
+    const size_t x = (size_t)(1 + sp.wmax_x - sp.wmin_x) * sizeof(float4) + (size_t)(sp.n_x + 2 * sp.wmax_x) * sizeof(float);
+    const size_t y = (size_t)(1 + sp.wmax_y - sp.wmin_y) * sizeof(float4) + (size_t)(sp.n_y + 2 * sp.wmax_y) * sizeof(float);
+    return (x > y ? x : y) + 16;
+}
+static int launch_sync_stage_generic(const float* img_cm, const float* img, float* c_v_raw, float* c_h_raw, const SyncParams& sp,
+                                     cudaStream_t st) {
+    k_colsum_generic<<<(sp.n_x + 127) / 128, 128, 0, st>>>(img, sp.n_y, sp.n_x, c_v_raw);
+    k_rowsum_generic<<<(sp.n_y + 127) / 128, 128, 0, st>>>(img_cm, sp.n_y, sp.n_x, c_h_raw);
+    k_fir_sigma_generic<<<2, 32, 0, st>>>(sp, c_v_raw, c_h_raw);
+    const int ctas = (sp.n_x + kBetaThreads - 1) / kBetaThreads + (sp.n_y + kBetaThreads - 1) / kBetaThreads;
+    k_beta<true><<<dim3(1, ctas), kBetaThreads, beta_generic_smem(sp), st>>>(sp);
     return TSDR_OK;
 }
 
@@ -638,9 +654,14 @@ extern "C" {
 
 int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     TSDR_REQUIRE(out, "out is NULL");
-    TSDR_REQUIRE(n_y == kRenderH && n_x == kRenderW,
-                 "SyncXY is only built for the %dx%d rendering size (src/GUI.jl:10), got %dx%d", kRenderH, kRenderW, n_y, n_x);
-    TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
+    // the reference builds SyncXY for size(image), whatever it is (src/FrameSynchronisation.jl:31-47); an image too small
+    // for one window width (1 + wmax - wmin < 1) makes its zeros(T, 1+wmax-wmin, n) / findmax throw
+    TSDR_REQUIRE(n_y >= 4 && n_x >= 4 && n_y <= kSyncGenericMaxN && n_x <= kSyncGenericMaxN,
+                 "SyncXY needs 4 <= n_y, n_x <= %d (got %dx%d)", kSyncGenericMaxN, n_y, n_x);
+    TSDR_REQUIRE((int)floor((double)n_y / 4.0) >= (int)ceil(1.0 / 100.0 * (double)n_y) &&
+                 (int)floor((double)n_x / 4.0) >= (int)ceil(5.0 / 100.0 * (double)n_x),
+                 "image %dx%d leaves no blanking width to search (the reference's beta tables would be empty)", n_y, n_x);
+    TSDR_TIER1_DEVICE(); int rc = TSDR_OK; (void)rc;
     tsdr_sync* s = new (std::nothrow) tsdr_sync();
     if (!s) return TSDR_ERR_NOMEM;
     memset(s, 0, sizeof(*s));
@@ -652,10 +673,12 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     sp.wmin_x = (int)ceil(5.0 / 100.0 * (double)n_x); sp.wmax_x = (int)floor((double)n_x / 4.0);
     const size_t nbx = (size_t)(1 + sp.wmax_x - sp.wmin_x) * n_x, nby = (size_t)(1 + sp.wmax_y - sp.wmin_y) * n_y;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_img_cm, (size_t)kRenderN * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_img, (size_t)kRenderN * 4);
+    const size_t n_img = (size_t)n_y * n_x;
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_img_cm, n_img * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_img, n_img * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cv, (size_t)kBands * n_x * 4);
     if (e == cudaSuccess) e = allow_max_dynamic_smem(k_project);
+    if (e == cudaSuccess) e = allow_max_dynamic_smem(k_beta<true>);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_ch, n_y * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cfv, n_x * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cfh, n_y * 4);
@@ -689,11 +712,16 @@ int tsdr_sync_bounds(const tsdr_sync* s, int* wmin_y, int* wmax_y, int* wmin_x, 
 int tsdr_vsync_f32(tsdr_sync* s, const float* img_colmajor, int* s_y, int* s_x) {
     TSDR_REQUIRE(s && img_colmajor && s_y && s_x, "NULL argument");
     TSDR_DEVICE(s->device);
-    TSDR_CUDA(cudaMemcpyAsync(s->d_img_cm, img_colmajor, (size_t)kRenderN * 4, cudaMemcpyHostToDevice, 0));
-    // column-major 600x800 == row-major 800x600 -> scan order 600x800
-    dim3 tg((kRenderH + 31) / 32, (kRenderW + 31) / 32), tb(32, 8);
-    k_transpose<<<tg, tb>>>(s->d_img_cm, s->d_img, kRenderW, kRenderH);
-    launch_sync_stage(s->d_img, 1, s->d_cv, s->d_ch, s->sp, 0);
+    const int n_y = s->n_y, n_x = s->n_x;
+    TSDR_CUDA(cudaMemcpyAsync(s->d_img_cm, img_colmajor, (size_t)n_y * n_x * 4, cudaMemcpyHostToDevice, 0));
+    // column-major n_y x n_x == row-major n_x x n_y -> scan order n_y x n_x
+    dim3 tg((n_y + 31) / 32, (n_x + 31) / 32), tb(32, 8);
+    k_transpose<<<tg, tb>>>(s->d_img_cm, s->d_img, n_x, n_y);
+    if (n_y == kRenderH && n_x == kRenderW) launch_sync_stage(s->d_img, 1, s->d_cv, s->d_ch, s->sp, 0);
+    else {
+        TSDR_REQUIRE(beta_generic_smem(s->sp) <= kMaxDynSmem, "SyncXY %dx%d needs more shared memory than an SM has", n_y, n_x);
+        launch_sync_stage_generic(s->d_img_cm, s->d_img, s->d_cv, s->d_ch, s->sp, 0);
+    }
     k_sync_carry<<<1, 32>>>(s->d_best, 1, s->d_off, s->d_off + 1, nullptr, nullptr);
     TSDR_CUDA(cudaGetLastError());
     int off[2];

@@ -136,6 +136,43 @@ def test_vsync_matches_oracle_with_stale_beta_y(integer):
     sg.close()
 
 
+def _stripe_frame_any(n_y, n_x, seed, integer):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 8, size=(n_y, n_x)).astype(np.float32) if integer else rng.random((n_y, n_x)).astype(np.float32)
+    r0, c0 = int(rng.integers(0, n_y)), int(rng.integers(0, n_x))
+    img[np.arange(r0, r0 + max(1, n_y // 15)) % n_y, :] = 16.0 if integer else 1.5
+    img[:, np.arange(c0, c0 + max(1, n_x // 7)) % n_x] = 16.0 if integer else 1.5
+    return img
+
+
+@pytest.mark.parametrize("shape", [(1481, 2720), (2250, 4400), (525, 800), (628, 1056), (37, 53), (4, 4), (600, 801), (1589, 2800)])
+def test_vsync_any_image_size_matches_oracle(shape):
+    # SyncXY(image) takes size(image) (src/FrameSynchronisation.jl:31-47); the headless recipe calls it on the full
+    # y_t x x_t frame (production/investigate_data.jl:196-197).  Offsets, both beta tables and the stale-beta_y state
+    # bit-exact for every size, incl. projections longer than 1024 (Base's pairwise sum)
+    n_y, n_x = shape
+    so = orc.SyncXY(n_y, n_x)
+    sg = tsdr.SyncXY(np.zeros(shape, np.float32))
+    assert (sg.wmin_y, sg.wmax_y, sg.wmin_x, sg.wmax_x) == (so.wmin_y, so.wmax_y, so.wmin_x, so.wmax_x)
+    for k in range(3):
+        img = _stripe_frame_any(n_y, n_x, 7 * k + n_x, integer=(k != 1))
+        ref = orc.vsync(img, so)
+        got = tsdr.vsync(img, sg)
+        assert got == ref
+        if k == 0:
+            assert got[0] == 1
+        assert np.array_equal(sg.beta_x, so.beta_x())
+        assert np.array_equal(sg.beta_y, so.beta_y())
+    sg.close()
+
+
+def test_syncxy_rejects_images_without_a_search_range():
+    # 1 + wmax - wmin < 1: the reference's zeros(T, 1+wmax-wmin, n) / findmax of an empty table throw
+    for shape in [(3, 800), (600, 3), (2, 2)]:
+        with pytest.raises(tsdr.TempestError):
+            tsdr.SyncXY(np.zeros(shape, np.float32))
+
+
 def test_vsync_nan_frame():
     so, sg = orc.SyncXY(), tsdr.SyncXY()
     img = _stripe_frame(5, False)
@@ -452,6 +489,28 @@ def test_extract_configuration_recovers_refresh(synth):
     assert y_hat == 1 / (fv_hat * (m / Fs))
     name = list(tsdr.find_closest_configuration(y_hat, fv_hat))[0]
     assert tsdr.allVideoConfigurations[name].refresh == 60.0
+
+
+# ------------------------------------------------------------- cfg 1: headless replay of a capture
+@pytest.mark.parametrize("fmt", ["single", "short", "double"])
+def test_cfg1_replay_of_a_dat_capture_matches_oracle(synth, tmp_path, fmt):
+    # BASELINE configs[0]: the bundled dumpIQ_0.dat (missing from the checkout) replayed through the headless recipe.
+    # Stand-in: a seeded 10^7-sample capture of the mode the docs name for that file (VideoMode(2800,1589,~60.14),
+    # docs/src/gui.md:29), written and read back in each .dat format of src/DatBinaryFiles.jl
+    Fs, (x_t, y_t, fv) = 20e6, (2800, 1589, 60.14)
+    iq = synth.make_iq(10_000_000, Fs, x_t, y_t, fv, seed=314)
+    path = str(tmp_path / "dumpIQ_standin.dat")
+    tsdr.writeComplexBinary(iq, path, fmt)
+    sigRx = tsdr.readComplexBinary(path, fmt).astype(np.complex64)
+    if fmt == "single":
+        assert np.array_equal(sigRx, iq)
+    got = tsdr.investigate_capture(sigRx, Fs)
+    ref = orc.investigate_capture(sigRx, Fs, tsdr.find_closest_configuration, offset=420_000)
+    for k in ("fv", "posMax", "m", "y_t", "name", "idx"):       # detected line / frame counts: equal
+        assert got[k] == ref[k], k
+    assert tuple(got["vsync"]) == tuple(ref["vsync"])            # full-size SyncXY (1589 x 2800)
+    assert np.array_equal(got["image"], ref["image"]) and np.array_equal(got["image_synced"], ref["image_synced"])
+    assert abs(got["fv"] - fv) < 0.5 and tsdr.allVideoConfigurations[got["name"]].refresh == 60
 
 
 # ------------------------------------------------------------- sharded integration (cfg 5 logic)

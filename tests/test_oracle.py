@@ -225,3 +225,29 @@ def test_get_spectrum_family_against_numpy():
     assert s.dtype == np.float64 and s.shape == (256, n // 256) and np.allclose(t, np.arange(n // 256) * 256.0)
     ref = np.fft.fftshift(np.abs(np.fft.fft(seg, axis=1)) ** 2, axes=1).T
     assert np.abs(s - ref).max() <= 2e-6 * ref.max()
+
+
+@pytest.mark.parametrize("shape", [(1300, 2100), (53, 37), (600, 800)])
+def test_vsync_c_vs_numpy_any_size(shape):
+    # generic SyncXY sizes, incl. projections longer than 1024 elements (Base.sum goes pairwise there): the C oracle and
+    # the independent numpy restatement agree bit for bit on offsets and both beta tables
+    import oracle_np as onp
+    n_y, n_x = shape
+    rng = np.random.default_rng(n_y)
+    so, sn = orc.SyncXY(n_y, n_x), onp.SyncXY(n_y, n_x)
+    for k in range(2):
+        img = rng.random(shape).astype(np.float32)
+        img[(n_y // 3 + 5 * k) % n_y, :] = 2.0
+        img[:, (n_x // 2 + 9 * k) % n_x] = 2.0
+        assert orc.vsync(img, so) == tuple(onp.vsync(img, sn))
+        assert np.array_equal(so.beta_x(), sn.beta_x) and np.array_equal(so.beta_y(), sn.beta_y)
+
+
+def test_base_sum_is_pairwise_beyond_1024():
+    import oracle_np as onp
+    rng = np.random.default_rng(2)
+    for n in (5, 800, 1024, 1025, 4400):
+        c = rng.random(n).astype(np.float32)
+        beta = orc.fill_beta(c, 1, 1)          # beta[0, c] = ((Sigma - s)/(2(n-1)) + s/2)^2 exposes Sigma
+        want = onp.fill_beta(c, 1, 1)
+        assert np.array_equal(beta, want)
