@@ -2,10 +2,11 @@
 #
 # Julia is not installed in the build image, so this file has never been executed there; it is
 # kept mechanical and mirrors, call for call, the ctypes binding in ../api.py that the GPU
-# parity tests exercise.  Usage from the reference (see INTEGRATION.md):
+# parity tests exercise (tests/test_abi.py checks every ccall's symbol, arity and argument types
+# against include/tempest_b200.h).  Usage from the reference (see INTEGRATION.md):
 #
 #     include("TempestSDRB200.jl"); using .TempestSDRB200
-#     TempestSDRB200.use!(TempestSDR)      # rebinds amDemod, sig_to_image, ... to the GPU versions
+#     TempestSDRB200.use!(TempestSDR)      # adds Float32 methods of amDemod, sig_to_image, ... that run on the GPU
 #
 # Every function keeps the reference signature (src/TempestSDR.jl:21-47 exports).  Matrices are
 # plain column-major Julia Arrays, ComplexF32 vectors are passed as they are (interleaved re, im).
@@ -13,7 +14,8 @@ module TempestSDRB200
 
 export amDemod, invert_amDemod, sig_to_image, downgradeImage, naiveResampler, init_resampler,
        calculate_autocorrelation, zoom_autocorr, SyncXY, vsync, Chain, push!, image, offsets,
-       AtomicCircularBuffer, circ_put!, circ_take!, push_ring!, getSpectrum, getWelch, getWaterfall
+       AtomicCircularBuffer, circ_put!, circ_take!, push_ring!, getSpectrum, getWelch, getWaterfall,
+       Comm, comm_unique_id, allreduce!, integrate_device!
 
 const LIB = get(ENV, "TEMPEST_B200_LIB", joinpath(@__DIR__, "..", "libtempest_b200.so"))
 const RENDERING_SIZE = (600, 800)                      # src/GUI.jl:10
@@ -280,12 +282,106 @@ function push_ring!(c::Chain, ring::AtomicCircularBuffer{T}; timeout_ms = -1) wh
     return Int(n[])
 end
 
-# Rebind the reference module's DSP functions to the GPU versions (same names, same signatures).
-function use!(ref::Module)
-    for f in (:amDemod, :invert_amDemod, :sig_to_image, :downgradeImage, :naiveResampler, :init_resampler,
-              :calculate_autocorrelation, :zoom_autocorr, :vsync)
-        Core.eval(ref, :($f(args...; kw...) = $(getfield(TempestSDRB200, f))(args...; kw...)))
+# ---- multi-GPU combine of a long integration (BASELINE cfg 5; src/GUI.jl:175 is linear in the frames) --------------
+# One communicator per GPU.  One Julia process per GPU (Distributed / MPI.jl / several julia's): rank 0 calls
+# comm_unique_id(), ships the 128 bytes to the others by any means, every rank builds Comm(id, nranks, rank; device).
+comm_unique_id() = (id = Vector{UInt8}(undef, 128);
+                    GC.@preserve id check(ccall((:tsdr_comm_get_unique_id, LIB), Cint, (Ptr{Cvoid},), pointer(id))); id)
+
+mutable struct Comm
+    handle::Ptr{Cvoid}
+    nranks::Int
+    rank::Int
+    function Comm(id::Vector{UInt8}, nranks::Integer, rank::Integer; device = 0)
+        length(id) == 128 || throw(ArgumentError("unique id must be 128 bytes"))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve id check(ccall((:tsdr_comm_init_rank, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Ptr{Cvoid}),
+                                    h, device, nranks, rank, pointer(id)))
+        c = new(h[], nranks, rank)
+        finalizer(x -> ccall((:tsdr_comm_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), c)
+        return c
     end
+end
+
+# imageOut <- sum over ranks of weight_rank * imageOut_rank (weight = α^(frames after this rank's block)); asynchronous
+allreduce!(c::Chain, comm::Comm, weight = 1.0f0) =
+    check(ccall((:tsdr_chain_allreduce, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cfloat), c.handle, comm.handle, weight))
+
+# one rank's share of a sharded integration in one call: reset, prime with the halo frame, push the device buffers
+# (CuArray pointers or any device addresses), combine.  halo == C_NULL for the first block, comm === nothing for 1 GPU.
+function integrate_device!(c::Chain, halo::Ptr{Cvoid}, halo_samples::Integer, bufs::Vector{Ptr{Cvoid}}, samples::Vector{Csize_t};
+                           comm::Union{Comm,Nothing} = nothing, weight = 1.0f0)
+    n = Ref{Cint}(0)
+    GC.@preserve bufs samples check(ccall((:tsdr_chain_integrate_device, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Ptr{Cvoid}}, Ptr{Csize_t}, Cint, Ptr{Cvoid}, Cfloat, Ptr{Cint}),
+        c.handle, halo, halo_samples, pointer(bufs), pointer(samples), length(bufs),
+        comm === nothing ? C_NULL : comm.handle, weight, n))
+    return Int(n[])
+end
+
+# ---- vsync on the REFERENCE's own SyncXY{Float32} -------------------------------------------------------------------
+# coreProcessing builds the reference's struct itself (src/GUI.jl:136) and hands it to vsync (:171).  Its whole state is
+# the pair of public tables β_x / β_y (src/FrameSynchronisation.jl:25-30): s_y is read from the β_y the PREVIOUS call left
+# there (:66), so that part stays on the host exactly as the reference does it, the GPU computes both new tables and
+# s_x, and the tables are copied back into the struct's arrays.  Device handles are stateless here: one per image size.
+const _SYNC_POOL = Dict{Tuple{Int,Int},Tuple{Ptr{Cvoid},ReentrantLock}}()
+const _SYNC_POOL_LOCK = ReentrantLock()
+function _pooled_sync(n_y::Int, n_x::Int)
+    lock(_SYNC_POOL_LOCK) do
+        get!(_SYNC_POOL, (n_y, n_x)) do
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:tsdr_sync_create, LIB), Cint, (Cint, Cint, Ptr{Ptr{Cvoid}}), n_y, n_x, h))
+            (h[], ReentrantLock())
+        end
+    end
+end
+
+function vsync_into(image::AbstractMatrix{Float32}, sync)          # sync: anything with Float32 matrices β_x, β_y
+    img = image isa Matrix{Float32} ? image : collect(image)
+    s_y = findmax(sync.β_y)[2][2]                                  # :66 -- the table of the previous call
+    (handle, lk) = _pooled_sync(size(img, 1), size(img, 2))
+    sy = Ref{Cint}(0); sx = Ref{Cint}(0)
+    βx = sync.β_x; βy = sync.β_y
+    lock(lk) do
+        GC.@preserve img βx βy begin
+            check(ccall((:tsdr_vsync_f32, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}), handle, pointer(img), sy, sx))
+            check(ccall((:tsdr_sync_get_beta, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), handle, pointer(βx), pointer(βy)))
+        end
+    end
+    return (s_y, Int(sx[]))
+end
+
+# ---- drop-in: zero changes to GUI.jl ---------------------------------------------------------------------------------
+# The reference's DSP functions are untyped or generic in T (src/Demodulation.jl:26, src/Resampler.jl:117,124,
+# src/Autocorrelations.jl:23, src/FrameSynchronisation.jl:56).  use! adds, IN THE MODULE THAT OWNS EACH FUNCTION, a method
+# for the Float32 argument types the GUI actually passes (GUI.jl:128-129,164-171; :64-73).  Those methods are strictly
+# more specific than the reference's, so dispatch picks them for Float32 data and every other element type keeps the
+# reference's own code -- nothing is overwritten, no name is rebound.  (The functions reach TempestSDR through
+# `@reexport using .Resampler` etc., src/TempestSDR.jl:27-46, which is why the methods must be evaluated in the submodules.)
+function use!(ref::Module)
+    B = @__MODULE__
+    Core.eval(ref, quote                                   # Demodulation.jl is included at TempestSDR's top level (:21-23)
+        amDemod(sig::Array{ComplexF32}) = $B.amDemod(sig)
+        invert_amDemod(sig::Array{ComplexF32}) = $B.invert_amDemod(sig)
+    end)
+    Core.eval(ref.Resampler, quote
+        sig_to_image(sig::AbstractVector{Float32}, y_t, x_t) = $B.sig_to_image(sig, y_t, x_t)
+        downgradeImage(image::Matrix{Float32}) = $B.downgradeImage(image)
+        naiveResampler(sigOut::Vector{Float32}, sigId::Vector{Float32}, upCoeff) = $B.naiveResampler(sigOut, sigId, upCoeff)
+        init_resampler(::Type{Float32}, bufferSize::Int, upCoeff::Int) = $B.init_resampler(Float32, bufferSize, upCoeff)
+    end)
+    Core.eval(ref.Autocorrelations, quote
+        calculate_autocorrelation(x::Vector{Float32}, Fs, minDelay, maxDelay, scale = :log) =
+            $B.calculate_autocorrelation(x, Fs, minDelay, maxDelay, scale)
+    end)
+    Core.eval(ref.FrameSynchronisation, quote                # the reference's own SyncXY{Float32}: tables stay in the struct
+        vsync(image::AbstractMatrix{Float32}, sync::SyncXY{Float32}) = $B.vsync_into(image, sync)
+    end)
+    Core.eval(ref.GetSpectrum, quote
+        getSpectrum(fs, sig::Vector{ComplexF32}; N = nothing) = $B.getSpectrum(fs, sig; N = N)
+        getWelch(fe, sig::Vector{ComplexF32}; sizeFFT = 1024) = $B.getWelch(fe, sig; sizeFFT = sizeFFT)
+        getWaterfall(fe, sig::Vector{ComplexF32}; sizeFFT = 1024) = $B.getWaterfall(fe, sig; sizeFFT = sizeFFT)
+    end)
     return nothing
 end
 
