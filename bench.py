@@ -527,7 +527,7 @@ def int16_ingest_measure(ctx, ch, ring, host_ring, wl, S, frames, steps, warmup)
                     "d2h_bytes_per_step": R * 4, "steps": k}}
 
 
-def measure_integration(ctx, steps, warmup, check=True):
+def measure_integration(ctx, steps, warmup, check=True, full_res=False):
     """cfg 5: a step = one 1000-frame integration.  Rank g takes a contiguous block of frames (parallel.shard_contiguous),
     primes the sync state with its halo frame, runs the chain over its block from a zero accumulator, and ONE all-reduce
     behind the C ABI (tsdr_chain_allreduce: NCCL PreMulSum, the tail weight alpha^(frames after the block) folded into
@@ -547,7 +547,8 @@ def measure_integration(ctx, steps, warmup, check=True):
     k0, k1 = parallel.shard_contiguous(total, world, rank)
     ring = [synth.make_iq_torch(n_ech, Fs, x_t, y_t, fv, dev, seed=500 + 10 * rank + i, t0=i * n_ech) for i in range(wl["ring"])]
     torch.cuda.synchronize()
-    ch = tsdr.Chain(Fs, cfg, alpha=alpha, max_samples=n_ech, device=ctx.local_rank, stream=ctx.stream)
+    ch = tsdr.Chain(Fs, cfg, alpha=alpha, max_samples=n_ech, device=ctx.local_rank, stream=ctx.stream, full_res=full_res)
+    img_floats = ch.accumulator_ptr()[1]
     weight = parallel.ema_tail_weight(alpha, total - k1)
     # this rank's block as a list of (device pointer, samples): whole buffers of the ring, then the remainder
     bufs, cnts, done, i = [], [], 0, 0
@@ -612,7 +613,10 @@ def measure_integration(ctx, steps, warmup, check=True):
 
     breakdown = {"reset+halo_prime_ms": timed(prime_only), "block_without_collective_ms": timed(block_only)}
     if ctx.comm:
-        breakdown["allreduce_alone_ms"] = timed(lambda: ctx.comm.allreduce_chain(ch, weight))
+        t_ar = timed(lambda: ctx.comm.allreduce_chain(ch, weight))
+        breakdown["allreduce_alone_ms"] = t_ar
+        # bus bandwidth of the all-reduce (2(N-1)/N x bytes per rank / time): NVLink-bound only for the full-resolution accumulator
+        breakdown["allreduce_busbw_gbs"] = 2.0 * (world - 1) / world * img_floats * 4 / (t_ar * 1e-3) / 1e9
     ch.set_profiling(True)
     block_only()
     stage_ms, pushes = ch.kernel_times()
@@ -621,18 +625,20 @@ def measure_integration(ctx, steps, warmup, check=True):
                                       "pushes": int(pushes)}
     render_ms = stage_ms[0] / max(pushes, 1)
     frames_per_launch = (k1 - k0 + (1 if halo else 0)) / max(pushes, 1)
-    algo = (8.0 * S + 4.0 * R) * frames_per_launch
-    chain_bytes = (8.0 * S + 12.0 * R) * total
-    roofline = {"bound": "hbm", "kernel": "k_render", "achieved": algo / (render_ms * 1e-3) / 1e9, "peak": ctx.hbm_peak,
+    Rimg = img_floats                                  # pixels of imageOut: 600*800, or y_t*x_t at full resolution
+    algo = (8.0 * S + 4.0 * Rimg) * frames_per_launch
+    chain_bytes = (8.0 * S + 12.0 * Rimg) * total
+    roofline = {"bound": "hbm", "kernel": "k_render_full" if full_res else "k_render", "achieved": algo / (render_ms * 1e-3) / 1e9, "peak": ctx.hbm_peak,
                 "unit": "GB/s", "frac": algo / (render_ms * 1e-3) / 1e9 / ctx.hbm_peak,
                 "algorithmic_bytes_per_launch": algo, "kernel_ms_per_launch": render_ms,
                 "chain_step": {"algorithmic_bytes": chain_bytes, "achieved": chain_bytes / (step_ms * 1e-3) / 1e9,
                                "frac_per_gpu": chain_bytes / (step_ms * 1e-3) / 1e9 / ctx.hbm_peak / world}}
-    out = {"workload": wl["name"], "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": steps,
-           "ms_per_step": step_ms, "scaling": "strong", "frames_per_step": total, "samples_per_frame": S,
+    out = {"workload": wl["name"] + (" -- FULL RESOLUTION (no downgradeImage: frames, SyncXY and imageOut at 2250x4400)" if full_res else ""),
+           "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": steps,
+           "ms_per_step": step_ms, "scaling": "strong", "accumulator_bytes": img_floats * 4, "frames_per_step": total, "samples_per_frame": S,
            "frames_this_rank": k1 - k0, "frames_per_push": per_buf, "pushes_this_rank": len(bufs),
            "gpu_launches": int(launches), "collectives": int(collectives),
-           "collective": "tsdr_chain_allreduce: NCCL all-reduce (PreMulSum) of the 1.92 MB accumulator, bound by the library "
+           "collective": "tsdr_chain_allreduce: NCCL all-reduce (PreMulSum) of the %.2f MB accumulator, bound by the library " % (img_floats * 4 / 1e6) +
                          "itself behind the C ABI; torch.distributed only carried the communicator id" if ctx.comm else "none (1 rank)",
            "clocks": clocks, "breakdown": breakdown, "roofline": roofline}
     ch.close()
@@ -640,14 +646,14 @@ def measure_integration(ctx, steps, warmup, check=True):
     torch.cuda.empty_cache()
     if check:
         try:
-            out.update(check_integration(ctx, cfg, Fs, alpha))
+            out.update(check_integration(ctx, cfg, Fs, alpha, full_res))
         except Exception as exc:
             out["matches_sequential"] = None
             out["check_error"] = repr(exc)[:300]
     return out
 
 
-def check_integration(ctx, cfg, Fs, alpha):
+def check_integration(ctx, cfg, Fs, alpha, full_res=False):
     """correctness of the sharded integration at the cfg 5 shape: T frames, the same capture on every rank (rank 0
     generates it, torch.distributed carries it: test data, not the data path), each rank integrates its block and the
     all-reduce combines; rank 0 runs the CPU oracle over all T frames SEQUENTIALLY and compares image and offsets"""
@@ -656,7 +662,7 @@ def check_integration(ctx, cfg, Fs, alpha):
     from tempestsdr_b200 import parallel
     world, rank = ctx.world, ctx.rank
     S = tsdr.getImageDuration(cfg, Fs)
-    T = max(8, 2 * world)
+    T = max(4, world) if full_res else max(8, 2 * world)
     if rank == 0:
         iq = synth.make_iq_torch(T * S, Fs, cfg.width, cfg.height, cfg.refresh, dev, seed=4242)
     else:
@@ -665,7 +671,7 @@ def check_integration(ctx, cfg, Fs, alpha):
         dist.broadcast(iq, src=0)
     torch.cuda.synchronize()
     k0, k1 = parallel.shard_contiguous(T, world, rank)
-    ch = tsdr.Chain(Fs, cfg, alpha=alpha, max_samples=(k1 - k0) * S, device=ctx.local_rank, stream=ctx.stream)
+    ch = tsdr.Chain(Fs, cfg, alpha=alpha, max_samples=(k1 - k0) * S, device=ctx.local_rank, stream=ctx.stream, full_res=full_res)
     base = iq.data_ptr()
     halo = base + (k0 - 1) * S * 8 if k0 > 0 else 0
     ch.integrate_device(halo, S, [base + k0 * S * 8], [(k1 - k0) * S], comm=ctx.comm, weight=parallel.ema_tail_weight(alpha, T - k1))
@@ -682,8 +688,13 @@ def check_integration(ctx, cfg, Fs, alpha):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import orc
         z = iq.cpu().numpy().view(np.complex64).reshape(-1)
-        ref, _, sy_ref, sx_ref = orc.chain_buffer(z, Fs, cfg.width, cfg.height, cfg.refresh, alpha, orc.SyncXY(),
-                                                  np.zeros((600, 800), np.float32), publish=False, nthreads=orc.num_threads())
+        if full_res:
+            ref, _, sy_ref, sx_ref = orc.chain_buffer_fullres(z, Fs, cfg.width, cfg.height, cfg.refresh, alpha,
+                                                              orc.SyncXY(cfg.height, cfg.width),
+                                                              np.zeros((cfg.height, cfg.width), np.float32))
+        else:
+            ref, _, sy_ref, sx_ref = orc.chain_buffer(z, Fs, cfg.width, cfg.height, cfg.refresh, alpha, orc.SyncXY(),
+                                                      np.zeros((600, 800), np.float32), publish=False, nthreads=orc.num_threads())
         sy_all = [v for _, a, _ in sorted(offs) for v in a]
         sx_all = [v for _, _, b in sorted(offs) for v in b]
         offsets_ok = sy_all == [int(v) for v in sy_ref] and sx_all == [int(v) for v in sx_ref]
@@ -893,6 +904,7 @@ def main():
             for name, fn in (("cfg2" if args.workload == "cfg3" else "cfg3",
                               lambda: measure_chain(ctx, "cfg2" if args.workload == "cfg3" else "cfg3", min(args.steps, 20), 3, headline=False)),
                              ("cfg5", lambda: measure_integration(ctx, max(2, min(args.steps, 5)), 3)),
+                             ("cfg5_fullres", lambda: measure_integration(ctx, 2, 3, full_res=True)),
                              ("cfg4", lambda: measure_sweep(ctx, max(2, min(args.steps, 8)), 3))):
                 try:
                     also[name] = fn()

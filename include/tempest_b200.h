@@ -74,8 +74,9 @@ int tsdr_naive_resampler_f32(float* out, const float* in, size_t n, int up);
 
 /* init_resampler(Float32, bufferSize, upCoeff) -> resampler!(out, in): FFT-domain integer upsampler
  * (zero-stuff, FFT, * H, IFFT, 2*upCoeff*real).  src/Resampler.jl:26-62, filter from initLPF :83-99.
- * The GPU FFT engine handles bufferSize*upCoeff = 2^k, 32 <= 2^k <= 2^24; other sizes return
- * TSDR_ERR_UNSUPPORTED.  apply enforces the reference's size assertion (:47). */
+ * Any length N = bufferSize*upCoeff the reference accepts: powers of two in [32, 2^24] directly, every other N as two
+ * chirp-z transforms on the next power of two >= 2N-1 (N <= 2^23); beyond that TSDR_ERR_UNSUPPORTED.
+ * apply enforces the reference's size assertion (:47). */
 typedef struct tsdr_upsampler tsdr_upsampler;
 int tsdr_upsampler_create(size_t buffer_size, int up_coeff, tsdr_upsampler** out);
 int tsdr_upsampler_apply_f32(tsdr_upsampler* u, float* out, size_t n_out, const float* in, size_t n_in);
@@ -127,6 +128,13 @@ typedef struct tsdr_chain tsdr_chain;
 #define TSDR_CHAIN_NO_ALIGN    2u /* do_align = false (GUI.jl:170): skip vsync/circshift */
 #define TSDR_CHAIN_SUM         4u /* plain frame sum instead of the EMA (long integrations, cfg 5) */
 #define TSDR_CHAIN_NO_OVERLAP  8u /* run every kernel on the primary stream (no two-stream pipelining) */
+/* Full-resolution mode: the loop body WITHOUT downgradeImage -- frames, SyncXY, circshift and
+ * imageOut all at y_t x x_t (what GUI.jl:168 computes before `|> downgradeImage`; SyncXY takes any image size,
+ * FrameSynchronisation.jl:31-47).  imageOut is then y_t*x_t floats (39.6 MB at 4400x2250): tsdr_chain_read_image /
+ * _deliver / _accumulator / tsdr_chain_allreduce all work on that size (tsdr_chain_image_size reports it), and
+ * tsdr_chain_read_image_downgraded gives the 600 x 800 view the GUI displays (imresize of the averaged image).
+ * ComplexF32 input only. */
+#define TSDR_CHAIN_FULLRES    16u
 
 /* stream: a cudaStream_t to run on (e.g. the caller's), or NULL for a private one. */
 int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t, double fv, float alpha,
@@ -174,8 +182,12 @@ int tsdr_chain_sync(tsdr_chain* c);
  * on its internal auxiliary stream: after this, an event recorded on the primary stream
  * covers every kernel of every push so far. */
 int tsdr_chain_flush(tsdr_chain* c);
-/* imageOut (600 x 800, column-major) -> host; synchronises the stream */
+/* imageOut (600 x 800, or y_t x x_t in full-resolution mode; column-major) -> host; synchronises the stream */
 int tsdr_chain_read_image(tsdr_chain* c, float* out_colmajor);
+/* size of imageOut: 600 x 800, or y_t x x_t with TSDR_CHAIN_FULLRES */
+int tsdr_chain_image_size(tsdr_chain* c, int* n_y, int* n_x);
+/* downgradeImage(imageOut) = imresize(imageOut, (600, 800)) (src/Resampler.jl:124-126), column-major; synchronises */
+int tsdr_chain_read_image_downgraded(tsdr_chain* c, float* out600x800_colmajor);
 /* per-frame (s_y, s_x) of the last pushed buffer -> host (up to max entries) */
 int tsdr_chain_read_offsets(tsdr_chain* c, int* s_y, int* s_x, int max, int* n_frames);
 /* every published imageOut of the last buffer (needs TSDR_CHAIN_PUBLISH_ALL):

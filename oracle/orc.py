@@ -350,6 +350,25 @@ def chain_buffer(iq, Fs, x_t, y_t, fv, alpha, sync, image_out, publish=True, nth
     return _from_cm(acc, RENDER_H, RENDER_W), fr, sy[:nb], sx[:nb]
 
 
+def chain_buffer_fullres(iq, Fs, x_t, y_t, fv, alpha, sync, image_out, do_align=True):
+    """the loop body of coreProcessing (src/GUI.jl:163-178) WITHOUT `|> downgradeImage` (full-resolution mode,
+    SURVEY 8(f) rank 4): frames, SyncXY (sync = SyncXY(y_t, x_t)), circshift and the EMA all at y_t x x_t.
+    Returns (imageOut, [every intermediate imageOut], s_y list, s_x list)."""
+    S = frame_samples(Fs, fv)
+    env = amDemod(iq)
+    acc = np.asarray(image_out, np.float32)
+    sy, sx, pub = [], [], []
+    for n in range(env.size // S):
+        img = sig_to_image(env[n * S:(n + 1) * S], y_t, x_t)
+        if do_align:
+            t = vsync(img, sync)
+            img = circshift(img, t[0], t[1])
+            sy.append(t[0]); sx.append(t[1])
+        acc = ema(acc, img, alpha)
+        pub.append(acc.copy())
+    return acc, pub, sy, sx
+
+
 def investigate_capture(sigRx, Fs, find_closest_configuration, offset=420_000, N=500):
     """the headless recipe of production/investigate_data.jl:37-97,159-206 with the oracle's functions (checker for
     BASELINE configs[0]); find_closest_configuration is the host-side table lookup (src/VideoConfigurations.jl:117-124)"""

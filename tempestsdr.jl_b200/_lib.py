@@ -14,6 +14,7 @@ TSDR_CHAIN_PUBLISH_ALL = 1
 TSDR_CHAIN_NO_ALIGN = 2
 TSDR_CHAIN_SUM = 4
 TSDR_CHAIN_NO_OVERLAP = 8
+TSDR_CHAIN_FULLRES = 16
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int)
@@ -66,6 +67,8 @@ SIGNATURES = {
     "tsdr_chain_sync": (C.c_int, [_vp]),
     "tsdr_chain_flush": (C.c_int, [_vp]),
     "tsdr_chain_read_image": (C.c_int, [_vp, _vp]),
+    "tsdr_chain_image_size": (C.c_int, [_vp, _ip, _ip]),
+    "tsdr_chain_read_image_downgraded": (C.c_int, [_vp, _vp]),
     "tsdr_chain_read_offsets": (C.c_int, [_vp, _vp, _vp, C.c_int, _ip]),
     "tsdr_chain_read_scores": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _ip]),
     "tsdr_chain_read_published": (C.c_int, [_vp, _vp, C.c_int, _ip]),

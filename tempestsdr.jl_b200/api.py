@@ -321,11 +321,12 @@ class Chain:
     """
 
     def __init__(self, Fs, config, alpha=0.1, max_samples=None, device=0, publish_all=False, do_align=True,
-                 sum_mode=False, stream=None, overlap=True):
+                 sum_mode=False, stream=None, overlap=True, full_res=False):
         if max_samples is None:
             max_samples = getImageDuration(config, Fs)
         flags = (_lib.TSDR_CHAIN_PUBLISH_ALL if publish_all else 0) | (0 if do_align else _lib.TSDR_CHAIN_NO_ALIGN) \
-            | (_lib.TSDR_CHAIN_SUM if sum_mode else 0) | (0 if overlap else _lib.TSDR_CHAIN_NO_OVERLAP)
+            | (_lib.TSDR_CHAIN_SUM if sum_mode else 0) | (0 if overlap else _lib.TSDR_CHAIN_NO_OVERLAP) \
+            | (_lib.TSDR_CHAIN_FULLRES if full_res else 0)
         h = C.c_void_p()
         check(_lib.load().tsdr_chain_create(C.byref(h), int(device), float(Fs), int(config.width), int(config.height),
                                             float(config.refresh), float(alpha), int(max_samples), flags,
@@ -422,9 +423,21 @@ class Chain:
         """primary stream waits (device side) for the chain's auxiliary stream"""
         check(_lib.load().tsdr_chain_flush(self._h))
 
+    def image_size(self):
+        """(rows, cols) of imageOut: RENDERING_SIZE, or (y_t, x_t) for a full_res chain"""
+        a, b = C.c_int(0), C.c_int(0)
+        check(_lib.load().tsdr_chain_image_size(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def image(self):
-        out = np.empty(RENDERING_SIZE, np.float32, order="F")
+        out = np.empty(self.image_size(), np.float32, order="F")
         check(_lib.load().tsdr_chain_read_image(self._h, _ptr(out)))
+        return out
+
+    def image_downgraded(self):
+        """downgradeImage(imageOut): the 600 x 800 view of a full_res chain's accumulator"""
+        out = np.empty(RENDERING_SIZE, np.float32, order="F")
+        check(_lib.load().tsdr_chain_read_image_downgraded(self._h, _ptr(out)))
         return out
 
     def offsets(self, max_frames=65536):
@@ -449,7 +462,8 @@ class Chain:
         """every intermediate imageOut of the last buffer (non_blocking_put!, src/GUI.jl:177)"""
         if max_frames is None:
             max_frames = self.max_samples // self.S
-        buf = np.empty((max_frames, RENDERING_SIZE[1], RENDERING_SIZE[0]), np.float32)
+        h, w = self.image_size()
+        buf = np.empty((max_frames, w, h), np.float32)
         n = C.c_int(0)
         check(_lib.load().tsdr_chain_read_published(self._h, _ptr(buf), max_frames, C.byref(n)))
         k = min(n.value, max_frames)

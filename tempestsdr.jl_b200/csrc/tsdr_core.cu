@@ -779,6 +779,14 @@ struct tsdr_chain {
     RenderParams rp;
     SyncParams sp;
     size_t smem_bytes;
+    // image the chain accumulates: 600 x 800 (downgradeImage), or y_t x x_t with TSDR_CHAIN_FULLRES
+    bool fullres;
+    int img_h, img_w;
+    size_t img_n, img_cap;      // pixels per image; pixels the accumulator / snapshot buffers were allocated for
+    int n_bands;                // 32-row bands of the image
+    RenderFullParams rfp;
+    size_t smem_full;
+    float* d_cvraw;             // [F][img_w] folded column sums (full-resolution mode)
     // device memory
     float* d_iq2[2];    // two staging buffers for push_host (max_samples + pad each)
     float* d_frames2[2]; // 2 x [max_frames][600][800]: render of buffer b+1 overlaps the sync/accumulate of buffer b
@@ -814,6 +822,7 @@ static void chain_free_frames(tsdr_chain* c) {
     cudaFree(c->d_frames2[1]); c->d_frames2[1] = nullptr;
     cudaFree(c->d_published); c->d_published = nullptr;
     cudaFree(c->d_cv); c->d_cv = nullptr;
+    cudaFree(c->d_cvraw); c->d_cvraw = nullptr;
     cudaFree(c->d_ch); c->d_ch = nullptr;
     cudaFree(c->d_cfv); c->d_cfv = nullptr;
     cudaFree(c->d_cfh); c->d_cfh = nullptr;
@@ -875,24 +884,63 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
         if ((size_t)(wmax + 4) * sizeof(double) <= 20 * 1024) { G = cand; win = std::max(win, wmax); }
     }
     const size_t smem = (size_t)(win + 4) * sizeof(double);
-    if (smem > 200 * 1024) {
+    if (smem > 200 * 1024 && !(c->flags & TSDR_CHAIN_FULLRES)) {
         set_error("frame window of %d samples does not fit shared memory (Fs/fv/y_t = %.1f samples per line)", win,
                   (double)S / y_t);
         return TSDR_ERR_UNSUPPORTED;
     }
     const int max_frames = (int)(c->max_samples / (size_t)S);
     TSDR_REQUIRE(max_frames >= 1, "max_samples (%zu) holds no complete frame of %lld samples", c->max_samples, (long long)S);
+    const bool fullres = (c->flags & TSDR_CHAIN_FULLRES) != 0;
+    const int img_h = fullres ? y_t : kRenderH, img_w = fullres ? x_t : kRenderW;
+    const size_t img_n = (size_t)img_h * img_w;
+    const int n_bands = (img_h + kBandRows - 1) / kBandRows;
+    SyncParams spn;
+    memset(&spn, 0, sizeof(spn));
+    gaussian_taps(spn.h);
+    spn.n_x = img_w; spn.n_y = img_h;
+    spn.wmin_y = (int)ceil(1.0 / 100.0 * (double)img_h); spn.wmax_y = (int)floor((double)img_h / 4.0);
+    spn.wmin_x = (int)ceil(5.0 / 100.0 * (double)img_w); spn.wmax_x = (int)floor((double)img_w / 4.0);
+    size_t smem_full = 0;
+    int pix_per_cta = 0;
+    if (fullres) {
+        TSDR_REQUIRE(img_h >= 4 && img_w >= 4 && img_h <= kSyncGenericMaxN && img_w <= kSyncGenericMaxN &&
+                     spn.wmax_y >= spn.wmin_y && spn.wmax_x >= spn.wmin_x,
+                     "full-resolution mode needs 4 <= y_t, x_t <= %d (got %dx%d)", kSyncGenericMaxN, y_t, x_t);
+        if (!(c->flags & TSDR_CHAIN_NO_ALIGN) && beta_generic_smem(spn) > kMaxDynSmem) {
+            set_error("SyncXY of a %dx%d frame needs more shared memory than an SM has", y_t, x_t);
+            return TSDR_ERR_UNSUPPORTED;
+        }
+        // pixels per CTA of k_render_full: 4096, fewer when the capture is so oversampled that the window would not fit
+        pix_per_cta = 4096;
+        while (pix_per_cta > 256 && ((double)pix_per_cta * m1.sf + 8.0) * sizeof(double) > 96.0 * 1024.0) pix_per_cta /= 2;
+        smem_full = (size_t)((double)pix_per_cta * (m1.identity ? 1.0 : m1.sf) + 8.0) * sizeof(double) + 64;
+        if (smem_full > kMaxDynSmem) { set_error("capture oversampled %.0f times: the sample window of a pixel run does not fit shared memory", m1.sf); return TSDR_ERR_UNSUPPORTED; }
+    }
 
     TSDR_DEVICE(c->device);
-    if (max_frames > c->max_frames || !c->d_frames2[0]) {
+    if (img_n > c->img_cap) {   // imageOut, its transposed copy and the delivery snapshots follow the image size
+        cudaFree(c->d_acc); cudaFree(c->d_tmp); cudaFree(c->d_snap[0]); cudaFree(c->d_snap[1]);
+        c->d_acc = c->d_tmp = c->d_snap[0] = c->d_snap[1] = nullptr; c->img_cap = 0;
+        TSDR_CUDA(cudaMalloc(&c->d_acc, img_n * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_tmp, img_n * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_snap[0], img_n * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_snap[1], img_n * 4));
+        c->img_cap = img_n;
+        TSDR_CUDA(cudaMemsetAsync(c->d_acc, 0, img_n * 4, c->stream));
+    } else if (img_n != c->img_n) {
+        TSDR_CUDA(cudaMemsetAsync(c->d_acc, 0, img_n * 4, c->stream));   // a different image size starts a fresh imageOut
+    }
+    if (max_frames > c->max_frames || !c->d_frames2[0] || img_n != c->img_n) {
         chain_free_frames(c);
-        TSDR_CUDA(cudaMalloc(&c->d_frames2[0], (size_t)max_frames * kRenderN * 4));
-        TSDR_CUDA(cudaMalloc(&c->d_frames2[1], (size_t)max_frames * kRenderN * 4));
-        if (c->flags & TSDR_CHAIN_PUBLISH_ALL) TSDR_CUDA(cudaMalloc(&c->d_published, (size_t)max_frames * kRenderN * 4));
-        TSDR_CUDA(cudaMalloc(&c->d_cv, (size_t)max_frames * kBands * kRenderW * 4));
-        TSDR_CUDA(cudaMalloc(&c->d_ch, (size_t)max_frames * kRenderH * 4));
-        TSDR_CUDA(cudaMalloc(&c->d_cfv, (size_t)max_frames * kRenderW * 4));
-        TSDR_CUDA(cudaMalloc(&c->d_cfh, (size_t)max_frames * kRenderH * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_frames2[0], (size_t)max_frames * img_n * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_frames2[1], (size_t)max_frames * img_n * 4));
+        if (c->flags & TSDR_CHAIN_PUBLISH_ALL) TSDR_CUDA(cudaMalloc(&c->d_published, (size_t)max_frames * img_n * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_cv, (size_t)max_frames * n_bands * img_w * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_cvraw, (size_t)max_frames * img_w * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_ch, (size_t)max_frames * img_h * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_cfv, (size_t)max_frames * img_w * 4));
+        TSDR_CUDA(cudaMalloc(&c->d_cfh, (size_t)max_frames * img_h * 4));
         TSDR_CUDA(cudaMalloc(&c->d_sigma, (size_t)max_frames * 2 * 4));
         TSDR_CUDA(cudaMalloc(&c->d_tickets, (size_t)max_frames * 4));
         TSDR_CUDA(cudaMemsetAsync(c->d_tickets, 0, (size_t)max_frames * 4, c->stream));
@@ -917,6 +965,8 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
 
     c->Fs = Fs; c->fv = fv; c->x_t = x_t; c->y_t = y_t; c->S = S; c->max_frames = max_frames;
     c->smem_bytes = smem;
+    c->fullres = fullres; c->img_h = img_h; c->img_w = img_w; c->img_n = img_n; c->n_bands = n_bands;
+    c->smem_full = smem_full;
     RenderParams& rp = c->rp;
     rp.S = S; rp.x_t = x_t; rp.y_t = y_t;
     rp.sf1 = m1.sf; rp.off1 = m1.off; rp.clamp1 = m1.clamp; rp.identity1 = m1.identity; rp.identity2 = identity2;
@@ -940,11 +990,15 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     c->smem_bytes_i16 = (size_t)(win + 8) * 12;
     TSDR_CUDA(allow_max_dynamic_smem(k_render<true>));
     TSDR_CUDA(allow_max_dynamic_smem(k_project));
+    if (fullres) {
+        TSDR_CUDA(allow_max_dynamic_smem(k_render_full));
+        TSDR_CUDA(allow_max_dynamic_smem(k_beta<true>));
+        RenderFullParams& rf = c->rfp;
+        rf.S = S; rf.P = P; rf.sf1 = m1.sf; rf.off1 = m1.off; rf.clamp1 = m1.clamp; rf.identity1 = m1.identity;
+        rf.safe_lo = rp.safe_lo; rf.safe_hi = rp.safe_hi; rf.pix_per_cta = pix_per_cta;
+    }
     SyncParams& sp = c->sp;
-    gaussian_taps(sp.h);
-    sp.n_x = kRenderW; sp.n_y = kRenderH;
-    sp.wmin_y = (int)ceil(1.0 / 100.0 * (double)kRenderH); sp.wmax_y = (int)floor((double)kRenderH / 4.0);
-    sp.wmin_x = (int)ceil(5.0 / 100.0 * (double)kRenderW); sp.wmax_x = (int)floor((double)kRenderW / 4.0);
+    sp = spn;
     sp.colpart = c->d_cv; sp.c_h = c->d_ch; sp.best = c->d_best; sp.beta_x = nullptr; sp.beta_y = nullptr;
     sp.cf_v = c->d_cfv; sp.cf_h = c->d_cfh; sp.sigma = c->d_sigma; sp.tickets = c->d_tickets;
     return TSDR_OK;
@@ -989,7 +1043,13 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     if (piped) TSDR_CUDA(cudaStreamWaitEvent(st, c->ev_free[par], 0));  // frames[par] released by the push before last
     mark(st);
     dim3 grid((kRenderH + rp.rows_per_cta - 1) / rp.rows_per_cta, nb);
-    if (i16) {
+    if (c->fullres) {
+        TSDR_REQUIRE(!i16, "full-resolution mode takes ComplexF32 samples");
+        RenderFullParams rf = c->rfp;
+        rf.iq = iq_dev; rf.n_ech = (int64_t)n; rf.frames = c->d_frames2[par];
+        const unsigned ctas = (unsigned)((rf.P + rf.pix_per_cta - 1) / rf.pix_per_cta);
+        k_render_full<<<dim3(ctas, nb), kRenderFullThreads, c->smem_full, st>>>(rf);
+    } else if (i16) {
         TSDR_REQUIRE(c->smem_bytes_i16 <= 200 * 1024, "frame window does not fit shared memory for Int16 input");
         k_render<true><<<grid, kRenderThreads, c->smem_bytes_i16, st>>>(rp);
     } else {
@@ -1003,15 +1063,24 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
         c->aux_busy = true;
     }
     const int align = !(c->flags & TSDR_CHAIN_NO_ALIGN);
-    if (align) { launch_sync_stage(rp.frames, nb, c->d_cv, c->d_ch, c->sp, st2); c->launches += 2; }
+    if (align && c->fullres) {
+        k_project_full<<<dim3(c->n_bands, nb), kProjFullThreads, 0, st2>>>(rp.frames, c->img_h, c->img_w, c->n_bands, c->d_cv, c->d_ch);
+        k_fold_bands<<<dim3((c->img_w + 127) / 128, nb), 128, 0, st2>>>(c->d_cv, c->n_bands, c->img_w, c->d_cvraw);
+        k_fir_sigma_generic<<<dim3(2, nb), 32, 0, st2>>>(c->sp, c->d_cvraw, c->d_ch);
+        const int ctas = (c->img_w + kBetaThreads - 1) / kBetaThreads + (c->img_h + kBetaThreads - 1) / kBetaThreads;
+        k_beta<true><<<dim3(nb, ctas), kBetaThreads, beta_generic_smem(c->sp), st2>>>(c->sp);
+        c->launches += 4;
+    } else if (align) { launch_sync_stage(rp.frames, nb, c->d_cv, c->d_ch, c->sp, st2); c->launches += 2; }
     mark(st2);
     AccumParams ap;
     ap.frames = rp.frames; ap.best = c->d_best; ap.acc = c->d_acc;
     ap.published = (c->flags & TSDR_CHAIN_PUBLISH_ALL) ? c->d_published : nullptr;
     ap.n_frames = nb; ap.alpha = c->alpha; ap.one_minus_alpha = 1.0f - c->alpha;
     ap.align = align; ap.sum_mode = (c->flags & TSDR_CHAIN_SUM) ? 1 : 0;
+    ap.n_y = c->img_h; ap.n_x = c->img_w;
     if (!prime) {
-        if (ap.align && !ap.sum_mode && !ap.published) k_accumulate<true><<<kRenderH, kAccThreads, 0, st2>>>(ap);
+        if (c->fullres) k_accumulate_full<<<dim3(c->img_h, (c->img_w + kAccThreads * kAccCols - 1) / (kAccThreads * kAccCols)), kAccThreads, 0, st2>>>(ap);
+        else if (ap.align && !ap.sum_mode && !ap.published) k_accumulate<true><<<kRenderH, kAccThreads, 0, st2>>>(ap);
         else k_accumulate<false><<<kRenderH, kAccThreads, 0, st2>>>(ap);
         c->launches += 1;
     }
@@ -1021,10 +1090,10 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
         // per-buffer delivery (non_blocking_put!(imageOut), GUI.jl:177): transpose to Julia layout and copy out, stream ordered
         const int op = c->out_parity;
         c->out_parity ^= 1;
-        dim3 tg((kRenderW + 31) / 32, (kRenderH + 31) / 32), tb(32, 8);
-        k_transpose<<<tg, tb, 0, st2>>>(c->d_acc, c->d_snap[op], kRenderH, kRenderW);
+        dim3 tg((c->img_w + 31) / 32, (c->img_h + 31) / 32), tb(32, 8);
+        k_transpose<<<tg, tb, 0, st2>>>(c->d_acc, c->d_snap[op], c->img_h, c->img_w);
         c->launches += 1;
-        TSDR_CUDA(cudaMemcpyAsync(host_image, c->d_snap[op], (size_t)kRenderN * 4, cudaMemcpyDeviceToHost, st2));
+        TSDR_CUDA(cudaMemcpyAsync(host_image, c->d_snap[op], c->img_n * 4, cudaMemcpyDeviceToHost, st2));
         TSDR_CUDA(cudaEventRecord(c->ev_out[op], st2));
     }
     if (piped) TSDR_CUDA(cudaEventRecord(c->ev_free[par], st2));
@@ -1070,10 +1139,7 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaMalloc(&c->d_snap[i], (size_t)kRenderN * 4);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
-    }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
@@ -1081,15 +1147,13 @@ int tsdr_chain_create(tsdr_chain** out, int device, double Fs, int x_t, int y_t,
         // the staging buffers themselves are allocated by the first host push (chain_stage): a chain that is only
         // fed device buffers never pays 2 x max_samples x 8 bytes of HBM for them
     }
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_acc, (size_t)kRenderN * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_tmp, (size_t)kRenderN * 4);
+    // imageOut, its transposed copy and the delivery snapshots are sized by chain_setup (they follow the image size)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_fy, kRenderH * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_dy, kRenderH * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_kd, kRenderW * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_win_lo, kRenderH * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_win_len, kRenderH * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_dx, kRenderW * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_acc, 0, (size_t)kRenderN * 4, c->stream);
     if (e != cudaSuccess) rc = cuda_fail(e, "tsdr_chain_create", __FILE__, __LINE__);
     if (rc == TSDR_OK) rc = chain_setup(c, Fs, x_t, y_t, fv);
     if (rc != TSDR_OK) { tsdr_chain_destroy(c); return rc; }
@@ -1115,7 +1179,7 @@ int tsdr_chain_reset(tsdr_chain* c) {
     TSDR_REQUIRE(c, "chain is NULL");
     TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
-    TSDR_CUDA(cudaMemsetAsync(c->d_acc, 0, (size_t)kRenderN * 4, c->stream));
+    TSDR_CUDA(cudaMemsetAsync(c->d_acc, 0, c->img_n * 4, c->stream));
     TSDR_CUDA(cudaMemsetAsync(c->d_best, 0, (size_t)(c->max_frames + 1) * 2 * 8, c->stream));
     // slot [0][1] = kBestInit (beta = 0 at centre 1): low word 0xffffffff, high word 0 -- set on the device so that
     // reset stays asynchronous (a sharded integration resets once per block and must not drain the stream)
@@ -1202,9 +1266,9 @@ static int chain_push_deliver(tsdr_chain* c, const void* iq_host, size_t n, int*
     else {
         const int op = c->out_parity;
         c->out_parity ^= 1;
-        dim3 tg((kRenderW + 31) / 32, (kRenderH + 31) / 32), tb(32, 8);
-        k_transpose<<<tg, tb, 0, c->stream>>>(c->d_acc, c->d_snap[op], kRenderH, kRenderW);
-        TSDR_CUDA(cudaMemcpyAsync(image_out_host, c->d_snap[op], (size_t)kRenderN * 4, cudaMemcpyDeviceToHost, c->stream));
+        dim3 tg((c->img_w + 31) / 32, (c->img_h + 31) / 32), tb(32, 8);
+        k_transpose<<<tg, tb, 0, c->stream>>>(c->d_acc, c->d_snap[op], c->img_h, c->img_w);
+        TSDR_CUDA(cudaMemcpyAsync(image_out_host, c->d_snap[op], c->img_n * 4, cudaMemcpyDeviceToHost, c->stream));
         TSDR_CUDA(cudaEventRecord(c->ev_out[op], c->stream));
     }
     return TSDR_OK;
@@ -1292,11 +1356,36 @@ int tsdr_chain_read_image(tsdr_chain* c, float* out_colmajor) {
     TSDR_REQUIRE(c && out_colmajor, "NULL argument");
     TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
-    dim3 tg((kRenderW + 31) / 32, (kRenderH + 31) / 32), tb(32, 8);
-    k_transpose<<<tg, tb, 0, c->stream>>>(c->d_acc, c->d_tmp, kRenderH, kRenderW);
+    dim3 tg((c->img_w + 31) / 32, (c->img_h + 31) / 32), tb(32, 8);
+    k_transpose<<<tg, tb, 0, c->stream>>>(c->d_acc, c->d_tmp, c->img_h, c->img_w);
     c->launches += 1;
     TSDR_CUDA(cudaGetLastError());
-    TSDR_CUDA(cudaMemcpyAsync(out_colmajor, c->d_tmp, (size_t)kRenderN * 4, cudaMemcpyDeviceToHost, c->stream));
+    TSDR_CUDA(cudaMemcpyAsync(out_colmajor, c->d_tmp, c->img_n * 4, cudaMemcpyDeviceToHost, c->stream));
+    TSDR_CUDA(cudaStreamSynchronize(c->stream));
+    return TSDR_OK;
+}
+
+int tsdr_chain_image_size(tsdr_chain* c, int* n_y, int* n_x) {
+    TSDR_REQUIRE(c, "chain is NULL");
+    if (n_y) *n_y = c->img_h;
+    if (n_x) *n_x = c->img_w;
+    return TSDR_OK;
+}
+
+int tsdr_chain_read_image_downgraded(tsdr_chain* c, float* out600x800_colmajor) {
+    TSDR_REQUIRE(c && out600x800_colmajor, "NULL argument");
+    TSDR_DEVICE(c->device);
+    { int rc = chain_join(c); if (rc) return rc; }
+    dim3 tg((c->img_w + 31) / 32, (c->img_h + 31) / 32), tb(32, 8);
+    k_transpose<<<tg, tb, 0, c->stream>>>(c->d_acc, c->d_tmp, c->img_h, c->img_w);   // scan order -> Julia layout
+    const ResizeMap my = make_map(c->img_h, kRenderH), mx = make_map(c->img_w, kRenderW);
+    // d_snap[] are img_n floats each, at least 600*800 only when the image is that large: use a scratch slot
+    void* d_small = nullptr;
+    { int rc = scratch(4, (size_t)kRenderN * 4, &d_small); if (rc) return rc; }
+    k_downgrade<<<ew_blocks(kRenderN), kEwThreads, 0, c->stream>>>(c->d_tmp, my, mx, my.clamp || mx.clamp, (float*)d_small);
+    c->launches += 2;
+    TSDR_CUDA(cudaGetLastError());
+    TSDR_CUDA(cudaMemcpyAsync(out600x800_colmajor, d_small, (size_t)kRenderN * 4, cudaMemcpyDeviceToHost, c->stream));
     TSDR_CUDA(cudaStreamSynchronize(c->stream));
     return TSDR_OK;
 }
@@ -1341,11 +1430,11 @@ int tsdr_chain_read_published(tsdr_chain* c, float* out, int max_frames, int* n_
     { int rc = chain_join(c); if (rc) return rc; }
     const int n = c->last_frames < max_frames ? c->last_frames : max_frames;
     if (n_frames) *n_frames = c->last_frames;
-    dim3 tg((kRenderW + 31) / 32, (kRenderH + 31) / 32), tb(32, 8);
+    dim3 tg((c->img_w + 31) / 32, (c->img_h + 31) / 32), tb(32, 8);
     for (int f = 0; f < n; ++f) {
-        k_transpose<<<tg, tb, 0, c->stream>>>(c->d_published + (size_t)f * kRenderN, c->d_tmp, kRenderH, kRenderW);
+        k_transpose<<<tg, tb, 0, c->stream>>>(c->d_published + (size_t)f * c->img_n, c->d_tmp, c->img_h, c->img_w);
         c->launches += 1;
-        TSDR_CUDA(cudaMemcpyAsync(out + (size_t)f * kRenderN, c->d_tmp, (size_t)kRenderN * 4, cudaMemcpyDeviceToHost, c->stream));
+        TSDR_CUDA(cudaMemcpyAsync(out + (size_t)f * c->img_n, c->d_tmp, c->img_n * 4, cudaMemcpyDeviceToHost, c->stream));
     }
     TSDR_CUDA(cudaGetLastError());
     TSDR_CUDA(cudaStreamSynchronize(c->stream));
@@ -1357,7 +1446,7 @@ int tsdr_chain_accumulator(tsdr_chain* c, void** dev_ptr, size_t* n_floats) {
     TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }  // later work on the primary stream sees the finished accumulator
     if (dev_ptr) *dev_ptr = c->d_acc;
-    if (n_floats) *n_floats = (size_t)kRenderN;
+    if (n_floats) *n_floats = c->img_n;
     return TSDR_OK;
 }
 
@@ -1372,7 +1461,7 @@ int tsdr_chain_scale_accumulator(tsdr_chain* c, float factor) {
     TSDR_REQUIRE(c, "chain is NULL");
     TSDR_DEVICE(c->device);
     { int rc = chain_join(c); if (rc) return rc; }
-    tsdr::k_scale<<<ew_blocks(kRenderN), kEwThreads, 0, c->stream>>>(c->d_acc, kRenderN, factor);
+    tsdr::k_scale<<<ew_blocks(c->img_n), kEwThreads, 0, c->stream>>>(c->d_acc, (int)c->img_n, factor);
     c->launches += 1;
     TSDR_CUDA(cudaGetLastError());
     return TSDR_OK;

@@ -197,6 +197,13 @@ struct FftParams {
     //         M >= 2 n_in - 1 point engine: x[j] conj(b[j]) -> FFT -> * FFT(b) (Hd) -> IFFT; |X[k]|^2 = |y[k]|^2
     //         because the final chirp factor has unit modulus.  b[j] = exp(i pi j^2 / n_in).
     const float2* chirp;   // [n_in] b[j]
+    // modes 4 / 5: init_resampler / resampler! for a length N = n_in*up that is NOT a power of two, as two chirp-z
+    // transforms on the M >= 2N-1 point engine.  4: zero-stuffed real input -> DFT_N -> * filt (Resampler.jl:51-53)
+    // -> W = conj(.);  5: W -> DFT_N -> out = gain * real(.)/N  (IDFT(Y) = conj(DFT(conj Y))/N, Resampler.jl:55-59)
+    const double2* filt;   // [N] H of initLPF, natural frequency order
+    float2* W;             // [N] conj(spectrum * H) between the two transforms
+    int64_t n_tot;         // N
+    float inv_n;           // 1/N
 };
 
 __device__ __forceinline__ float2 twiddle_n(const FftParams& p, int64_t t) {  // W_N^t, 0 <= t < N
@@ -230,6 +237,15 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_cols(FftParams p) {
         } else if (p.mode == 2) {
             v = make_float2(0.f, 0.f);
             if (j < p.n_in) v = cmul(__ldg(reinterpret_cast<const float2*>(p.x) + j), cconj(__ldg(p.chirp + j)));
+        } else if (p.mode == 4) {   // containerFFT[1:upCoeff:end] .= in, times conj(b[j])
+            v = make_float2(0.f, 0.f);
+            if (j < p.n_tot) {
+                const int64_t q = j / p.up;
+                if (q * p.up == j && q < p.n_in) { const float2 b = __ldg(p.chirp + j); const float xv = __ldg(p.x + q); v = make_float2(xv * b.x, -xv * b.y); }
+            }
+        } else if (p.mode == 5) {
+            v = make_float2(0.f, 0.f);
+            if (j < p.n_tot) v = cmul(p.W[j], cconj(__ldg(p.chirp + j)));
         } else if (2 * j + 1 < p.n_valid) v = __ldg(reinterpret_cast<const float2*>(p.x) + j);
         else { v.x = (2 * j < p.n_valid) ? __ldg(p.x + 2 * j) : 0.f; v.y = 0.f; }
         sm[lay(col, j1)] = v;
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(kFftThreads) k_fft_mid(FftParams p) {
         }
         return;
     }
-    if (p.mode == 1 || p.mode == 2) {
+    if (p.mode == 1 || p.mode == 2 || p.mode == 4 || p.mode == 5) {
         // inFFT[n] = inFFT[n] * H[n]: ComplexF32 * ComplexF64 in Float64, rounded to ComplexF32 (Resampler.jl:51-53);
         // the 1/M of the scaled inverse plan is applied here
         for (int e = tid; e < nrows * p.B; e += kFftThreads) {
@@ -376,6 +392,22 @@ __global__ void __launch_bounds__(kFftThreads) k_ifft_cols(FftParams p) {
         const int j1 = e / p.C, col = e - j1 * p.C;
         const int64_t j = (int64_t)j1 * p.B + j2_0 + col;
         if (p.mode == 1) { p.out[j] = p.gain * sm[lay(col, j1)].x; continue; }  // out[n] = 2*upCoeff*real(outFFT[n])  (Resampler.jl:57-59)
+        if (p.mode == 4) {
+            if (j < p.n_tot) {
+                const float2 X = cmul(sm[lay(col, j1)], cconj(__ldg(p.chirp + j)));      // DFT_N of the zero-stuffed input
+                const double2 h = __ldg(p.filt + j);
+                const double a = (double)X.x, b = (double)X.y;                            // ComplexF32 * ComplexF64 -> ComplexF32
+                p.W[j] = make_float2((float)(a * h.x - b * h.y), -(float)(a * h.y + b * h.x));
+            }
+            continue;
+        }
+        if (p.mode == 5) {
+            if (j < p.n_tot) {
+                const float2 z = cmul(sm[lay(col, j1)], cconj(__ldg(p.chirp + j)));
+                p.out[j] = p.gain * (z.x * p.inv_n);                                      // 2*upCoeff*real(ifft(.))
+            }
+            continue;
+        }
         if (p.mode == 2) {
             if (j < p.n_in) {
                 const float2 z = sm[lay(col, j1)];
@@ -734,12 +766,47 @@ static void host_fft(std::vector<double>& re, std::vector<double>& im, bool inve
 }
 }  // namespace tsdr
 
+namespace tsdr {
+// exp(i pi j^2 / N) with the phase reduced exactly (j^2 mod 2N in 128-bit integers)
+static void chirp_phase(size_t j, size_t N, double& c, double& sn) {
+    const unsigned long long q = (unsigned long long)(((unsigned __int128)j * j) % (2 * (unsigned __int128)N));
+    const long double ph = 3.14159265358979323846264338327950288L * (long double)q / (long double)N;
+    c = (double)cosl(ph); sn = (double)sinl(ph);
+}
+// DFT of any length in double: radix-2 for powers of two, chirp-z (Bluestein) on the next power of two otherwise
+static void host_dft_any(std::vector<double>& re, std::vector<double>& im, bool inverse) {
+    const size_t N = re.size();
+    if (is_pow2(N)) { host_fft(re, im, inverse); return; }
+    size_t M = 2; while (M < 2 * N - 1) M <<= 1;
+    std::vector<double> ar(M, 0.0), ai(M, 0.0), br(M, 0.0), bi(M, 0.0), cr(N), ci(N);
+    const double sgn = inverse ? -1.0 : 1.0;   // inverse: conjugate chirp
+    for (size_t j = 0; j < N; ++j) {
+        double c, sn; chirp_phase(j, N, c, sn); sn *= sgn;
+        cr[j] = c; ci[j] = sn;
+        ar[j] = re[j] * c + im[j] * sn; ai[j] = im[j] * c - re[j] * sn;    // x[j] * conj(b[j])
+        br[j] = c; bi[j] = sn;
+        if (j) { br[M - j] = c; bi[M - j] = sn; }
+    }
+    host_fft(ar, ai, false); host_fft(br, bi, false);
+    for (size_t k = 0; k < M; ++k) { const double r = ar[k] * br[k] - ai[k] * bi[k], i = ar[k] * bi[k] + ai[k] * br[k]; ar[k] = r; ai[k] = i; }
+    host_fft(ar, ai, true);
+    const double sc = inverse ? 1.0 / (double)N : 1.0;
+    for (size_t k = 0; k < N; ++k) {                                       // * conj(b[k])
+        re[k] = (ar[k] * cr[k] + ai[k] * ci[k]) * sc;
+        im[k] = (ai[k] * cr[k] - ar[k] * ci[k]) * sc;
+    }
+}
+}  // namespace tsdr
+
 struct tsdr_upsampler {
-    tsdr_autocorr_plan* plan;  // complex M-point engine (M = buffer_size * up)
+    tsdr_autocorr_plan* plan;  // complex engine: M = buffer_size * up points, or the chirp-z size Mb >= 2M-1 when M is not 2^k
     size_t n_in, M;
     int up;
+    bool bluestein;
+    size_t Mb;
     double2* d_H;
     float* d_in; float* d_out;
+    float2* d_chirp; double2* d_Hb; float2* d_W;   // chirp-z route only
     std::vector<double>* H;    // host copy, interleaved
 };
 
@@ -750,6 +817,7 @@ int tsdr_upsampler_destroy(tsdr_upsampler* u) {
     DeviceScope scope;
     if (u->plan) { scope.enter(u->plan->device); cudaStreamSynchronize(u->plan->stream); }
     cudaFree(u->d_H); cudaFree(u->d_in); cudaFree(u->d_out);
+    cudaFree(u->d_chirp); cudaFree(u->d_Hb); cudaFree(u->d_W);
     tsdr_autocorr_plan_destroy(u->plan);
     delete u->H;
     delete u;
@@ -761,17 +829,22 @@ int tsdr_upsampler_create(size_t buffer_size, int up_coeff, tsdr_upsampler** out
     *out = nullptr;
     TSDR_REQUIRE(buffer_size >= 1 && up_coeff >= 1, "bufferSize and upCoeff must be positive");
     const size_t M = buffer_size * (size_t)up_coeff;
-    if (!is_pow2(M) || M < 32 || M > ((size_t)1 << 24)) {
-        set_error("init_resampler: bufferSize*upCoeff = %zu is not a power of two in [32, 2^24]; the GPU FFT engine "
-                  "only handles those lengths", M);
+    TSDR_REQUIRE(M >= 2, "init_resampler: bufferSize*upCoeff must be at least 2");
+    // the reference takes any length (FFTW plans any N, src/Resampler.jl:26-40): powers of two in [32, 2^24] go straight
+    // through the engine, every other length as two chirp-z transforms on the next power of two >= 2N-1
+    const bool direct = is_pow2(M) && M >= 32;
+    size_t Mb = M;
+    if (!direct) { Mb = 32; while (Mb < 2 * M - 1) Mb <<= 1; }
+    if (Mb > ((size_t)1 << 24)) {
+        set_error("init_resampler: bufferSize*upCoeff = %zu needs a %zu-point transform; the engine stops at 2^24", M, Mb);
         return TSDR_ERR_UNSUPPORTED;
     }
     TSDR_TIER1_DEVICE(); int rc = TSDR_OK;
     tsdr_upsampler* u = new (std::nothrow) tsdr_upsampler();
     if (!u) return TSDR_ERR_NOMEM;
     memset(u, 0, sizeof(*u));
-    u->n_in = buffer_size; u->M = M; u->up = up_coeff;
-    if ((rc = tsdr_autocorr_plan_create(&u->plan, current_device(), 2 * M, nullptr))) { tsdr_upsampler_destroy(u); return rc; }
+    u->n_in = buffer_size; u->M = M; u->up = up_coeff; u->bluestein = !direct; u->Mb = Mb;
+    if ((rc = tsdr_autocorr_plan_create(&u->plan, current_device(), 2 * Mb, nullptr))) { tsdr_upsampler_destroy(u); return rc; }
     // initLPF (src/Resampler.jl:83-99): brick-wall magnitude, linear phase rounded to integers,
     // ifft, Blackman window, fft, (-1)^k.  (The reference's ifft runs in Float32; here it is
     // evaluated in double and rounded to Float32, a <= 1e-7 relative difference in h.)
@@ -783,19 +856,38 @@ int tsdr_upsampler_create(size_t buffer_size, int up_coeff, tsdr_upsampler** out
         const double th = gd * puls;
         re[k] = nearbyint(cos(th)); im[k] = nearbyint(sin(th));
     }
-    host_fft(re, im, true);
+    host_dft_any(re, im, true);
     for (size_t k = 0; k < M; ++k) {
         const double x = (double)k / (double)(M - 1) - 0.5;
         const double w = 0.42 + 0.5 * cos(2.0 * 3.14159265358979323846 * x) + 0.08 * cos(4.0 * 3.14159265358979323846 * x);
         re[k] = (double)(float)re[k] * w; im[k] = (double)(float)im[k] * w;
     }
-    host_fft(re, im, false);
+    host_dft_any(re, im, false);
     u->H = new std::vector<double>(2 * M);
     for (size_t k = 0; k < M; ++k) { const double sg = (k & 1) ? -1.0 : 1.0; (*u->H)[2 * k] = sg * re[k]; (*u->H)[2 * k + 1] = sg * im[k]; }
     cudaError_t e = cudaMalloc(&u->d_H, M * sizeof(double2));
     if (e == cudaSuccess) e = cudaMalloc(&u->d_in, (buffer_size + 4) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&u->d_out, M * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(u->d_H, u->H->data(), M * sizeof(double2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && u->bluestein) {
+        // b[j] = exp(i pi j^2 / N) (Float32 on the device) and FFT_Mb of its wrapped extension (double), as getSpectrum does
+        std::vector<float2> chirp(M);
+        std::vector<double> br(Mb, 0.0), bi(Mb, 0.0);
+        for (size_t j = 0; j < M; ++j) {
+            double c, sn; chirp_phase(j, M, c, sn);
+            chirp[j] = make_float2((float)c, (float)sn);
+            br[j] = c; bi[j] = sn;
+            if (j) { br[Mb - j] = c; bi[Mb - j] = sn; }
+        }
+        host_fft(br, bi, false);
+        std::vector<double2> Hb(Mb);
+        for (size_t k = 0; k < Mb; ++k) Hb[k] = make_double2(br[k], bi[k]);
+        e = cudaMalloc(&u->d_chirp, M * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&u->d_Hb, Mb * sizeof(double2));
+        if (e == cudaSuccess) e = cudaMalloc(&u->d_W, M * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMemcpy(u->d_chirp, chirp.data(), M * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(u->d_Hb, Hb.data(), Mb * sizeof(double2), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) { tsdr_upsampler_destroy(u); return cuda_fail(e, "tsdr_upsampler_create", __FILE__, __LINE__); }
     *out = u;
     return TSDR_OK;
@@ -817,12 +909,20 @@ int tsdr_upsampler_apply_f32(tsdr_upsampler* u, float* out, size_t n_out, const 
     cudaStream_t st = p->stream;
     TSDR_CUDA(cudaMemcpyAsync(u->d_in, in, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
     FftParams fp = p->fp;
-    fp.mode = 1; fp.x = u->d_in; fp.n_in = (int64_t)u->n_in; fp.up = u->up; fp.Hd = u->d_H;
+    fp.x = u->d_in; fp.n_in = (int64_t)u->n_in; fp.up = u->up;
     fp.gain = (float)(2 * u->up); fp.out = u->d_out; fp.n_valid = 0;
-    k_fft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
-    k_fft_mid<<<fp.A / 2 + 1, kFftThreads, p->smem_mid, st>>>(fp);
-    k_ifft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
-    p->launches += 3;
+    const int passes = u->bluestein ? 2 : 1;
+    for (int pass = 0; pass < passes; ++pass) {
+        if (!u->bluestein) { fp.mode = 1; fp.Hd = u->d_H; }
+        else {
+            fp.mode = 4 + pass; fp.Hd = u->d_Hb; fp.chirp = u->d_chirp; fp.filt = u->d_H; fp.W = u->d_W;
+            fp.n_tot = (int64_t)u->M; fp.inv_n = 1.0f / (float)u->M;
+        }
+        k_fft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
+        k_fft_mid<<<fp.A / 2 + 1, kFftThreads, p->smem_mid, st>>>(fp);
+        k_ifft_cols<<<fp.B / fp.C, kFftThreads, p->smem_cols, st>>>(fp);
+        p->launches += 3;
+    }
     TSDR_CUDA(cudaGetLastError());
     TSDR_CUDA(cudaMemcpyAsync(out, u->d_out, u->M * sizeof(float), cudaMemcpyDeviceToHost, st));
     TSDR_CUDA(cudaStreamSynchronize(st));

@@ -77,7 +77,10 @@ def test_naiveResampler():
     assert np.array_equal(out, orc.naiveResampler(s, 3))
 
 
-@pytest.mark.parametrize("n,up", [(256, 4), (1024, 8), (4096, 2), (16, 2)])
+@pytest.mark.parametrize("n,up", [(256, 4), (1024, 8), (4096, 2), (16, 2),
+                                  # lengths that are not powers of two (the reference plans any N with FFTW,
+                                  # production/test_resampler.jl:32-35): chirp-z route
+                                  (100, 3), (250, 2), (81, 3), (1000, 7), (33333, 3), (8, 2), (3, 1)])
 def test_init_resampler_matches_oracle(n, up):
     t = np.arange(n) / n
     x = (np.sin(2 * np.pi * 5 * t) + 0.5 * np.cos(2 * np.pi * 11 * t) + 0.1 * np.random.default_rng(n).normal(size=n)).astype(np.float32)
@@ -92,8 +95,20 @@ def test_init_resampler_matches_oracle(n, up):
     assert np.max(np.abs(got - ref)) <= 1e-5 * np.max(np.abs(ref))
     with pytest.raises(AssertionError):
         got_fn(got, x[:-1])                      # size assertion of the reference (Resampler.jl:47)
+
+
+def test_init_resampler_dispatch_and_limits():
+    x = np.linspace(0, 1, 300, dtype=np.float32)
+    fn = tsdr.init_resampler(x, 3)               # init_resampler(x::Vector{T}, upCoeff)  (Resampler.jl:65-68)
+    out = np.zeros(900, np.float32)
+    fn(out, x)
+    ref = np.zeros(900, np.float32)
+    orc.init_resampler(300, 3)(ref, x)
+    assert np.max(np.abs(out - ref)) <= 1e-5 * np.max(np.abs(ref))
+    with pytest.raises(TypeError):
+        tsdr.init_resampler(np.float64, 100, 3)  # only T = Float32 exists on the GPU
     with pytest.raises(tsdr.TempestError):
-        tsdr.init_resampler(np.float32, 100, 3)  # 300 is not a power of two: unsupported on the GPU engine
+        tsdr.init_resampler(np.float32, (1 << 23) + 1, 1)   # needs a 2^25-point transform: beyond the engine
 
 
 def test_fullScale_findmax():
@@ -489,6 +504,53 @@ def test_extract_configuration_recovers_refresh(synth):
     assert y_hat == 1 / (fv_hat * (m / Fs))
     name = list(tsdr.find_closest_configuration(y_hat, fv_hat))[0]
     assert tsdr.allVideoConfigurations[name].refresh == 60.0
+
+
+# ------------------------------------------------------------- full-resolution chain
+@pytest.mark.parametrize("Fs,mode,frames,alpha", [
+    (2.0e6, (1056, 628, 60.0), 3, 0.3),       # P > S: 1-D upsampling, clamped ends
+    (30.0e6, (832, 445, 85.0), 2, 0.1),       # S > P: 1-D downsampling
+    (20.0e6, (2576, 1125, 60.0), 2, 0.1),     # cfg 2 shape, x_t > 1024 (pairwise Sigma), several column chunks
+    (480000.0 * 50, (800, 600, 50.0), 2, 0.5),   # S == P: imresize copies
+])
+def test_fullres_chain_bit_exact(synth, Fs, mode, frames, alpha):
+    x_t, y_t, fv = mode
+    S = orc.frame_samples(Fs, fv)
+    n = S * frames + 9
+    ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=alpha, max_samples=n, publish_all=True, full_res=True)
+    assert ch.image_size() == (y_t, x_t)
+    so = orc.SyncXY(y_t, x_t)
+    acc = np.zeros((y_t, x_t), np.float32)
+    for b in range(2):   # two buffers: imageOut and the stale beta_y carry over
+        iq = synth.make_iq(n, Fs, x_t, y_t, fv, seed=21 + b, t0=b * n)
+        acc, pub, sy_ref, sx_ref = orc.chain_buffer_fullres(iq, Fs, x_t, y_t, fv, alpha, so, acc)
+        assert ch.push(iq) == frames
+        sy, sx = ch.offsets()
+        assert list(sy) == sy_ref and list(sx) == sx_ref
+        assert np.array_equal(ch.published(), np.stack(pub))
+        assert np.array_equal(ch.image(), acc)
+    assert np.array_equal(ch.image_downgraded(), orc.downgradeImage(acc))   # the 600 x 800 view the GUI shows
+    ch.close()
+
+
+def test_fullres_cfg5_shape_and_reconfigure(synth):
+    # BASELINE cfg 5 shape at full resolution: the 39.6 MB accumulator of the bandwidth-bound all-reduce case
+    Fs, (x_t, y_t, fv), alpha = 200e6, (4400, 2250, 30.0), 0.1
+    S = orc.frame_samples(Fs, fv)
+    iq = synth.make_iq(2 * S, Fs, x_t, y_t, fv, seed=56)
+    ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=alpha, max_samples=iq.size, full_res=True)
+    assert ch.push(iq) == 2
+    ref, _, sy_ref, sx_ref = orc.chain_buffer_fullres(iq, Fs, x_t, y_t, fv, alpha, orc.SyncXY(y_t, x_t), np.zeros((y_t, x_t), np.float32))
+    sy, sx = ch.offsets()
+    assert list(sy) == sy_ref and list(sx) == sx_ref
+    assert np.array_equal(ch.image(), ref)
+    assert ch.accumulator_ptr()[1] == x_t * y_t
+    # FLAG_CONFIG_UPDATE to another mode: a fresh imageOut of the new size
+    ch.configure(2.0e6, tsdr.VideoMode(1056, 628, 60.0))
+    assert ch.image_size() == (628, 1056) and not ch.image().any()
+    ch.close()
+    with pytest.raises(tsdr.TempestError):
+        tsdr.Chain(2e6, tsdr.VideoMode(1056, 3, 60.0), max_samples=10 ** 6, full_res=True)   # no search range: SyncXY would throw
 
 
 # ------------------------------------------------------------- cfg 1: headless replay of a capture
