@@ -154,5 +154,32 @@ def build(force=False, verbose=False):
     return SO
 
 
+def build_variant(tag, defines):
+    """libtempest_b200_<tag>.so with extra -D flags (same-box A/B of compile-time shapes with tools/ab_render.py):
+        python tempestsdr.jl_b200/build.py --variant s4 -DTSDR_PROJP_STAGES=4
+    Not the product library: no hash file, no SASS summary."""
+    vdir = os.path.join(OBJDIR, "variant_" + tag)
+    os.makedirs(vdir, exist_ok=True)
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    objs = []
+    for src, extra in UNITS:
+        obj = os.path.join(vdir, src.replace(".cu", ".o"))
+        cmd = [nvcc()] + ccbin + ARCH + [f for f in COMMON if f not in ("-Xptxas", "-v")] + extra + list(defines) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        objs.append(obj)
+    out = os.path.join(HERE, "libtempest_b200_%s.so" % tag)
+    cmd = [nvcc()] + ccbin + ARCH + ["-shared", "-o", out] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

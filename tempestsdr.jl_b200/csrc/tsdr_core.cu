@@ -611,12 +611,73 @@ static void gaussian_taps(float h[5]) {  // init_gaussian_filter(5) then convert
 
 static const unsigned long long kBestInit = 0x00000000ffffffffull;  // beta = 0 at centre 1: findmax of zeros
 
-static int launch_sync_stage(const float* frames, int n_frames, float* c_v, float* c_h, const SyncParams& sp,
+// SMs of the current device (persistent grids are sized by it); cached per device
+static int sm_count() {
+    static std::mutex mu;
+    static std::vector<std::pair<int, int>> seen;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& d : seen) if (d.first == dev) return d.second;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    seen.emplace_back(dev, n);
+    return n;
+}
+
+// TSDR_PROJ_MODE (read at every launch, so one process can time both): "legacy" = one CTA per (band, frame)
+// (k_project / k_project_full); unset or a number k >= 1 = the persistent kernel with k CTAs per SM (default 1).
+// The two produce bit-identical projections; the switch exists for same-box A/B timing (tools/ab_render.py).
+static int proj_ctas_per_sm() {
+    const char* e = getenv("TSDR_PROJ_MODE");
+    if (!e || !*e) return 2;
+    if (!strcmp(e, "legacy")) return 0;
+    const int k = atoi(e);
+    return k >= 1 && k <= 8 ? k : 2;
+}
+
+// Tensor map of a frame buffer seen as a [n_rows][n_x] Float32 matrix with boxes of one column group x one band
+// (k_project_p).  cuTensorMapEncodeTiled is a driver entry point: fetched through the runtime, the library still
+// links only cudart.  Returns false when the shape cannot be described (rows that are not 16-byte multiples, an image
+// smaller than one box) -- the caller then launches the non-TMA kernel.
+typedef CUresult (*tsdr_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_frames_tmap(CUtensorMap* m, const float* base, int n_x, size_t n_rows) {
+    static const tsdr_encode_tiled_fn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            fn = nullptr;
+        }
+        return (tsdr_encode_tiled_fn)fn;
+    }();
+    if (!encode || !base || (n_x & 3) || n_x < kGroupStride || n_rows < (size_t)kBandRows) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)n_x, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)n_x * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kGroupStride, (cuuint32_t)kBandRows};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// tmap: tensor map of `frames` (make_frames_tmap), or NULL -> the per-(band, frame) kernel.  Returns the number of launches.
+static int launch_sync_stage(const float* frames, const CUtensorMap* tmap, int n_frames, float* c_v, float* c_h, const SyncParams& sp,
                              cudaStream_t st) {
     (void)c_v; (void)c_h;
-    k_project<<<dim3(kBands, n_frames), kProjThreads, kProjSmem, st>>>(frames, sp);
+    const int per_sm = proj_ctas_per_sm();
+    int launches = 2;
+    if (per_sm == 0 || !tmap) k_project<<<dim3(kBands, n_frames), kProjThreads, kProjSmem, st>>>(frames, sp);
+    else {
+        const int items = kBands * n_frames;
+        const int grid = std::min(items, per_sm * sm_count());
+        k_project_p<false><<<grid, kProjThreads, kProjPSmem, st>>>(*tmap, sp, n_frames, kBands, kProjGroups);
+        k_fold_fir<<<n_frames, 256, 0, st>>>(sp);
+        launches = 3;
+    }
     k_beta<false><<<dim3(n_frames, kBetaCtasX + kBetaCtasY), kBetaThreads, 0, st>>>(sp);
-    return TSDR_OK;
+    return launches;
 }
 
 // SyncXY of any other image size: one frame, column-major image in img_cm, its scan-order copy in img
@@ -648,6 +709,8 @@ struct tsdr_sync {
     float* d_beta_x; float* d_beta_y;
     unsigned long long* d_best;  // [2][2]
     int* d_off;                  // [2]
+    CUtensorMap tmap;            // of d_img (600 x 800 only)
+    bool has_tmap;
 };
 
 extern "C" {
@@ -678,6 +741,7 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     if (e == cudaSuccess) e = cudaMalloc(&s->d_img, n_img * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cv, (size_t)kBands * n_x * 4);
     if (e == cudaSuccess) e = allow_max_dynamic_smem(k_project);
+    if (e == cudaSuccess) e = allow_max_dynamic_smem(k_project_p<false>);
     if (e == cudaSuccess) e = allow_max_dynamic_smem(k_beta<true>);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_ch, n_y * 4);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cfv, n_x * 4);
@@ -696,6 +760,7 @@ int tsdr_sync_create(int n_y, int n_x, tsdr_sync** out) {
     if (e != cudaSuccess) { tsdr_sync_destroy(s); return cuda_fail(e, "tsdr_sync_create", __FILE__, __LINE__); }
     sp.colpart = s->d_cv; sp.c_h = s->d_ch; sp.best = s->d_best; sp.beta_x = s->d_beta_x; sp.beta_y = s->d_beta_y;
     sp.cf_v = s->d_cfv; sp.cf_h = s->d_cfh; sp.sigma = s->d_sigma; sp.tickets = s->d_tickets;
+    s->has_tmap = n_y == kRenderH && n_x == kRenderW && make_frames_tmap(&s->tmap, s->d_img, n_x, (size_t)n_y);
     *out = s;
     return TSDR_OK;
 }
@@ -717,7 +782,7 @@ int tsdr_vsync_f32(tsdr_sync* s, const float* img_colmajor, int* s_y, int* s_x) 
     // column-major n_y x n_x == row-major n_x x n_y -> scan order n_y x n_x
     dim3 tg((n_y + 31) / 32, (n_x + 31) / 32), tb(32, 8);
     k_transpose<<<tg, tb>>>(s->d_img_cm, s->d_img, n_x, n_y);
-    if (n_y == kRenderH && n_x == kRenderW) launch_sync_stage(s->d_img, 1, s->d_cv, s->d_ch, s->sp, 0);
+    if (n_y == kRenderH && n_x == kRenderW) launch_sync_stage(s->d_img, s->has_tmap ? &s->tmap : nullptr, 1, s->d_cv, s->d_ch, s->sp, 0);
     else {
         TSDR_REQUIRE(beta_generic_smem(s->sp) <= kMaxDynSmem, "SyncXY %dx%d needs more shared memory than an SM has", n_y, n_x);
         launch_sync_stage_generic(s->d_img_cm, s->d_img, s->d_cv, s->d_ch, s->sp, 0);
@@ -787,6 +852,8 @@ struct tsdr_chain {
     RenderFullParams rfp;
     size_t smem_full;
     float* d_cvraw;             // [F][img_w] folded column sums (full-resolution mode)
+    CUtensorMap tmap_frames[2]; // d_frames2[i] as a [max_frames * img_h][img_w] matrix (k_project_p)
+    bool has_tmap;
     // device memory
     float* d_iq2[2];    // two staging buffers for push_host (max_samples + pad each)
     float* d_frames2[2]; // 2 x [max_frames][600][800]: render of buffer b+1 overlaps the sync/accumulate of buffer b
@@ -967,6 +1034,8 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     c->smem_bytes = smem;
     c->fullres = fullres; c->img_h = img_h; c->img_w = img_w; c->img_n = img_n; c->n_bands = n_bands;
     c->smem_full = smem_full;
+    c->has_tmap = make_frames_tmap(&c->tmap_frames[0], c->d_frames2[0], img_w, (size_t)max_frames * img_h) &&
+                  make_frames_tmap(&c->tmap_frames[1], c->d_frames2[1], img_w, (size_t)max_frames * img_h);
     RenderParams& rp = c->rp;
     rp.S = S; rp.x_t = x_t; rp.y_t = y_t;
     rp.sf1 = m1.sf; rp.off1 = m1.off; rp.clamp1 = m1.clamp; rp.identity1 = m1.identity; rp.identity2 = identity2;
@@ -990,7 +1059,9 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     c->smem_bytes_i16 = (size_t)(win + 8) * 12;
     TSDR_CUDA(allow_max_dynamic_smem(k_render<true>));
     TSDR_CUDA(allow_max_dynamic_smem(k_project));
+    TSDR_CUDA(allow_max_dynamic_smem(k_project_p<false>));
     if (fullres) {
+        TSDR_CUDA(allow_max_dynamic_smem(k_project_p<true>));
         TSDR_CUDA(allow_max_dynamic_smem(k_render_full));
         TSDR_CUDA(allow_max_dynamic_smem(k_beta<true>));
         RenderFullParams& rf = c->rfp;
@@ -1064,13 +1135,20 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     }
     const int align = !(c->flags & TSDR_CHAIN_NO_ALIGN);
     if (align && c->fullres) {
-        k_project_full<<<dim3(c->n_bands, nb), kProjFullThreads, 0, st2>>>(rp.frames, c->img_h, c->img_w, c->n_bands, c->d_cv, c->d_ch);
+        const int per_sm = proj_ctas_per_sm();
+        if (per_sm == 0 || !c->has_tmap) {   // e.g. rows that are not 16-byte multiples cannot be described by a tensor map
+            k_project_full<<<dim3(c->n_bands, nb), kProjFullThreads, 0, st2>>>(rp.frames, c->img_h, c->img_w, c->n_bands, c->d_cv, c->d_ch);
+        } else {
+            const int items = c->n_bands * nb;
+            const int grid = std::min(items, per_sm * sm_count());
+            k_project_p<true><<<grid, kProjThreads, kProjPSmem, st2>>>(c->tmap_frames[par], c->sp, nb, c->n_bands, (c->img_w + kProjGroupCols - 1) / kProjGroupCols);
+        }
         k_fold_bands<<<dim3((c->img_w + 127) / 128, nb), 128, 0, st2>>>(c->d_cv, c->n_bands, c->img_w, c->d_cvraw);
         k_fir_sigma_generic<<<dim3(2, nb), 32, 0, st2>>>(c->sp, c->d_cvraw, c->d_ch);
         const int ctas = (c->img_w + kBetaThreads - 1) / kBetaThreads + (c->img_h + kBetaThreads - 1) / kBetaThreads;
         k_beta<true><<<dim3(nb, ctas), kBetaThreads, beta_generic_smem(c->sp), st2>>>(c->sp);
         c->launches += 4;
-    } else if (align) { launch_sync_stage(rp.frames, nb, c->d_cv, c->d_ch, c->sp, st2); c->launches += 2; }
+    } else if (align) { c->launches += launch_sync_stage(rp.frames, c->has_tmap ? &c->tmap_frames[par] : nullptr, nb, c->d_cv, c->d_ch, c->sp, st2); }
     mark(st2);
     AccumParams ap;
     ap.frames = rp.frames; ap.best = c->d_best; ap.acc = c->d_acc;

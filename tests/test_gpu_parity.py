@@ -2,6 +2,8 @@
 oracle on the same seeded inputs.  Bars: bit-exact for everything the
 oracle pins in Float32/FP64 (envelope, resampling, projections, FIR, beta, offsets, EMA);
 stated tolerances for atan2 / log10 / FFT based results."""
+import os
+
 import numpy as np
 import pytest
 
@@ -208,6 +210,7 @@ CHAIN_CASES = [
     (8.0e6, (800, 600, 70.0), 3, 0.25),     # (600, 800): downgradeImage copies
     (30.0e6, (832, 445, 85.0), 2, 0.0),     # 1-D downsampling (S > P), alpha = 0
     (480000.0 * 50, (800, 600, 50.0), 2, 0.5),  # S == P: both resizes copy
+    (2.0e6, (800, 525, 60.0), 37, 0.1),     # 703 (band, frame) items: every persistent projection CTA walks several
 ]
 
 
@@ -229,6 +232,28 @@ def test_chain_bit_exact(synth, Fs, mode, frames, alpha):
         assert np.array_equal(ch.published(), fr_ref)
         assert np.array_equal(ch.image(), acc)
     ch.close()
+
+
+def test_chain_legacy_projection_kernel_agrees(synth, monkeypatch):
+    # TSDR_PROJ_MODE=legacy selects the one-CTA-per-(band, frame) projection kernels the persistent ones replaced
+    # (read at every launch): same offsets, same imageOut, at 1 and 3 persistent CTAs per SM
+    Fs, x_t, y_t, fv = 2.0e6, 1056, 628, 60.0
+    n = orc.frame_samples(Fs, fv) * 9 + 5
+    iq = synth.make_iq(n, Fs, x_t, y_t, fv, seed=77)
+    res = {}
+    for mode in ("legacy", "1", "3"):
+        monkeypatch.setenv("TSDR_PROJ_MODE", mode)
+        for full in (False, True):
+            ch = tsdr.Chain(Fs, tsdr.VideoMode(x_t, y_t, fv), alpha=0.2, max_samples=n, full_res=full)
+            ch.push(iq); ch.push(iq)
+            sy, sx = ch.offsets()
+            res[mode, full] = (np.asarray(sy).copy(), np.asarray(sx).copy(), ch.image().copy())
+            ch.close()
+    monkeypatch.delenv("TSDR_PROJ_MODE")
+    for mode in ("1", "3"):
+        for full in (False, True):
+            for a, b in zip(res["legacy", full], res[mode, full]):
+                assert np.array_equal(a, b), (mode, full)
 
 
 def test_chain_int16_push_matches_widened_float_push(synth):
@@ -512,6 +537,8 @@ def test_extract_configuration_recovers_refresh(synth):
     (30.0e6, (832, 445, 85.0), 2, 0.1),       # S > P: 1-D downsampling
     (20.0e6, (2576, 1125, 60.0), 2, 0.1),     # cfg 2 shape, x_t > 1024 (pairwise Sigma), several column chunks
     (480000.0 * 50, (800, 600, 50.0), 2, 0.5),   # S == P: imresize copies
+    (2.0e6, (1053, 627, 60.0), 2, 0.2),       # rows that are not 16-byte multiples: the non-TMA projection kernel
+    (2.0e6, (400, 300, 60.0), 33, 0.1),       # 330 (band, frame) items: persistent projection CTAs walk several
 ])
 def test_fullres_chain_bit_exact(synth, Fs, mode, frames, alpha):
     x_t, y_t, fv = mode

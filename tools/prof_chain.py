@@ -1,6 +1,6 @@
 """tools/prof_chain.py -- a few pushes of one workload through the chain, for ncu:
     ncu --set full --clock-control none --import-source on -k regex:k_render -s 2 -c 1 -o gpurun_out/prof python tools/prof_chain.py cfg3 4
-    python tools/prof_chain.py cfg3 4 [i16]"""
+    python tools/prof_chain.py cfg3 4 [i16|full]"""
 import importlib.util
 import os
 import sys
@@ -21,6 +21,7 @@ spec.loader.exec_module(synth)
 key = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 pushes = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 i16 = len(sys.argv) > 3 and sys.argv[3] == "i16"
+full = len(sys.argv) > 3 and sys.argv[3] == "full"   # TSDR_CHAIN_FULLRES (cfg5: 25 frames of 4400 x 2250 per push)
 wl = dict(bench.WORKLOADS[key])
 cfg = tsdr.VideoMode(wl["x_t"], wl["y_t"], wl["fv"])
 S = tsdr.getImageDuration(cfg, wl["Fs"])
@@ -35,7 +36,7 @@ if i16:
         q.append(t)
 st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
-ch = tsdr.Chain(wl["Fs"], cfg, alpha=0.1, max_samples=n_ech, stream=st.cuda_stream)
+ch = tsdr.Chain(wl["Fs"], cfg, alpha=0.1, max_samples=n_ech, stream=st.cuda_stream, full_res=full)
 for i in range(pushes):
     if i16:
         ch.push_device_i16(q[i % 2].data_ptr(), n_ech)
