@@ -543,7 +543,7 @@ def measure_integration(ctx, steps, warmup, check=True, full_res=False):
     S = tsdr.getImageDuration(cfg, Fs)
     per_buf = wl["frames_per_buf"]                    # frames per device buffer = frames per push
     n_ech = per_buf * S
-    total = wl["total_frames"]
+    total = int(os.environ.get("TSDR_BENCH_CFG5_FRAMES", wl["total_frames"]))   # override: shorter blocks per rank on few GPUs
     k0, k1 = parallel.shard_contiguous(total, world, rank)
     ring = [synth.make_iq_torch(n_ech, Fs, x_t, y_t, fv, dev, seed=500 + 10 * rank + i, t0=i * n_ech) for i in range(wl["ring"])]
     torch.cuda.synchronize()
@@ -579,14 +579,16 @@ def measure_integration(ctx, steps, warmup, check=True, full_res=False):
     elapsed_ms = e0.elapsed_time(e1)
     launches = ch.launch_count() - l0
     collectives = (ctx.comm.collectives() - c0) if ctx.comm else 0
-    t_end = time.perf_counter() + 0.2
-    while time.perf_counter() < t_end:
-        one_integration()
-        torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ctx.barrier()
     elapsed_ms = ctx.max_over_ranks(elapsed_ms)
     step_ms = elapsed_ms / steps
+    # keep the clock sampler running for ~0.2 s more.  Every integration contains a collective, so the number of extra
+    # iterations must be the SAME on every rank: it is derived from the max-over-ranks step time, never from a local
+    # wall clock (a rank leaving a wall-clock loop one iteration early leaves the others inside the all-reduce for good)
+    for _ in range(max(1, min(200, int(200.0 / max(step_ms, 1e-3))))):
+        one_integration()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ctx.barrier()
     value = total * S / (step_ms * 1e-3) / 1e6
 
     # ---- where a step goes: the pieces timed one by one (CUDA events on the chain's stream, a barrier in front) ----
@@ -857,10 +859,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg5_fullres"])
     ap.add_argument("--no-extras", action="store_true", help="skip the also / autocorr extras")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS["cfg5" if args.workload == "cfg5_fullres" else args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -872,12 +874,12 @@ def main():
 
     ctx = Ctx(rank, local_rank, world)
     base = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "vs_baseline": None, "data": "synthetic"}
-    if args.workload == "cfg5":
-        m = measure_integration(ctx, args.steps, args.warmup)
+    if args.workload in ("cfg5", "cfg5_fullres"):
+        m = measure_integration(ctx, args.steps, args.warmup, full_res=args.workload == "cfg5_fullres")
         out = dict(base, metric=METRIC, value=m["value"], unit="MS/s", ms_per_step=m["ms_per_step"], higher_is_better=True,
                    scaling="strong", dtype="f32 (f64 coordinates)",
                    config={"workload": m["workload"], "frames_per_step": m["frames_per_step"], "frames_per_push": m["frames_per_push"],
-                           "parallelism": "contiguous frame blocks, halo frame primed, one all-reduce of 1.92 MB per integration (C ABI, NCCL)",
+                           "parallelism": "contiguous frame blocks, halo frame primed, one all-reduce of %.2f MB per integration (C ABI, NCCL)" % (m["accumulator_bytes"] / 1e6),
                            "l2_policy": "ring of 2 distinct 1.3 GB device buffers (> 126 MB L2), no flush"},
                    clocks=m["clocks"], gpu_launches=m["gpu_launches"], roofline=m["roofline"], integration=m,
                    e2e={"value": None, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
@@ -901,6 +903,20 @@ def main():
                 out[k] = m[k]
         if not args.no_extras:
             also = {}
+            # The headline above is complete.  The extras below contain collectives (cfg 5); should one of them ever hang
+            # (a rank lost, a collective mismatch) the run must still end with its line: after TSDR_BENCH_EXTRAS_DEADLINE
+            # seconds (default 420) every rank leaves, rank 0 printing the headline with whatever extras had finished.
+            deadline = float(os.environ.get("TSDR_BENCH_EXTRAS_DEADLINE", "420"))
+
+            def _give_up():
+                if rank == 0:
+                    out["also"] = dict(also, timed_out="extras did not finish within %.0f s; legs present had completed" % deadline)
+                    emit(out)
+                os._exit(0)
+
+            watchdog = threading.Timer(deadline, _give_up)
+            watchdog.daemon = True
+            watchdog.start()
             for name, fn in (("cfg2" if args.workload == "cfg3" else "cfg3",
                               lambda: measure_chain(ctx, "cfg2" if args.workload == "cfg3" else "cfg3", min(args.steps, 20), 3, headline=False)),
                              ("cfg5", lambda: measure_integration(ctx, max(2, min(args.steps, 5)), 3)),
@@ -921,6 +937,10 @@ def main():
                     out["autocorr"] = bench_autocorr(ctx)
                 except Exception as exc:
                     out["autocorr"] = {"error": repr(exc)[:300]}
+    try:
+        watchdog.cancel()
+    except NameError:
+        pass
     ctx.close()
     if rank == 0:
         emit(out)

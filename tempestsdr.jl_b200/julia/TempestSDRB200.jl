@@ -301,7 +301,24 @@ mutable struct Comm
         finalizer(x -> ccall((:tsdr_comm_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), c)
         return c
     end
+    function Comm(handle::Ptr{Cvoid}, nranks::Integer, rank::Integer)      # a communicator made by comm_init_all
+        c = new(handle, nranks, rank)
+        finalizer(x -> ccall((:tsdr_comm_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), c)
+        return c
+    end
 end
+
+# ONE Julia process driving several GPUs of a box: a communicator per device (devices 0..n-1, or the ones listed);
+# collectives issued from one thread for several of them go between group_start() and group_end()
+function comm_init_all(n::Integer; devices::Union{Vector{Cint},Nothing} = nothing)
+    hs = Vector{Ptr{Cvoid}}(undef, n)
+    devices === nothing || length(devices) == n || throw(ArgumentError("devices must list n entries"))
+    GC.@preserve hs devices check(ccall((:tsdr_comm_init_all, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint, Ptr{Cint}),
+                                        pointer(hs), n, devices === nothing ? Ptr{Cint}(C_NULL) : pointer(devices)))
+    return [Comm(hs[r], n, r - 1) for r in 1:n]
+end
+group_start() = check(ccall((:tsdr_comm_group_start, LIB), Cint, ()))
+group_end() = check(ccall((:tsdr_comm_group_end, LIB), Cint, ()))
 
 # imageOut <- sum over ranks of weight_rank * imageOut_rank (weight = α^(frames after this rank's block)); asynchronous
 allreduce!(c::Chain, comm::Comm, weight = 1.0f0) =
