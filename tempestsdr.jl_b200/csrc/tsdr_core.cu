@@ -1062,6 +1062,10 @@ static int chain_setup(tsdr_chain* c, double Fs, int x_t, int y_t, double fv) {
     TSDR_CUDA(allow_max_dynamic_smem(k_project_p<false>));
     if (fullres) {
         TSDR_CUDA(allow_max_dynamic_smem(k_project_p<true>));
+        TSDR_CUDA(allow_max_dynamic_smem(k_accumulate_rows<false, false>));
+        TSDR_CUDA(allow_max_dynamic_smem(k_accumulate_rows<false, true>));
+        TSDR_CUDA(allow_max_dynamic_smem(k_accumulate_rows<true, false>));
+        TSDR_CUDA(allow_max_dynamic_smem(k_accumulate_rows<true, true>));
         TSDR_CUDA(allow_max_dynamic_smem(k_render_full));
         TSDR_CUDA(allow_max_dynamic_smem(k_beta<true>));
         RenderFullParams& rf = c->rfp;
@@ -1157,7 +1161,19 @@ static int chain_run(tsdr_chain* c, const float* iq_dev, size_t n, int* n_frames
     ap.align = align; ap.sum_mode = (c->flags & TSDR_CHAIN_SUM) ? 1 : 0;
     ap.n_y = c->img_h; ap.n_x = c->img_w;
     if (!prime) {
-        if (c->fullres) k_accumulate_full<<<dim3(c->img_h, (c->img_w + kAccThreads * kAccCols - 1) / (kAccThreads * kAccCols)), kAccThreads, 0, st2>>>(ap);
+        if (c->fullres) {
+            // whole source rows through a shared-memory ring when the rows are 16-byte multiples and fit the kernel's
+            // register tile (TSDR_ACC_MODE=legacy: the register-staged kernel, for A/B)
+            const char* am = getenv("TSDR_ACC_MODE");
+            const size_t smem = acc_row_smem(c->img_w, nb);
+            if (!(am && !strcmp(am, "legacy")) && (c->img_w & 3) == 0 && c->img_w <= kAccRowThreads * kAccRowCols && smem <= kMaxDynSmem)
+            {
+                if (ap.sum_mode) { if (ap.published) k_accumulate_rows<true, true><<<c->img_h, kAccRowThreads, smem, st2>>>(ap); else k_accumulate_rows<true, false><<<c->img_h, kAccRowThreads, smem, st2>>>(ap); }
+                else { if (ap.published) k_accumulate_rows<false, true><<<c->img_h, kAccRowThreads, smem, st2>>>(ap); else k_accumulate_rows<false, false><<<c->img_h, kAccRowThreads, smem, st2>>>(ap); }
+            }
+            else
+                k_accumulate_full<<<dim3(c->img_h, (c->img_w + kAccThreads * kAccCols - 1) / (kAccThreads * kAccCols)), kAccThreads, 0, st2>>>(ap);
+        }
         else if (ap.align && !ap.sum_mode && !ap.published) k_accumulate<true><<<kRenderH, kAccThreads, 0, st2>>>(ap);
         else k_accumulate<false><<<kRenderH, kAccThreads, 0, st2>>>(ap);
         c->launches += 1;

@@ -705,10 +705,23 @@ int tsdr_autocorr_plan_exec(tsdr_autocorr_plan* p, const float* x_dev, size_t in
     if (p->has_fft3 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) {
         if (p->n == p->N) p->f3.p1<<<p->f3.grid_p1, p->f3.threads, p->f3.smem_p1, st>>>(fp);
         else p->f3.p1_padded<<<p->f3.grid_p1, p->f3.threads, p->f3.smem_p1, st>>>(fp);
-        p->f3.p2<<<p->f3.grid_p2, p->f3.threads, p->f3.smem_p2, st>>>(fp);
-        p->f3.p3<<<p->f3.grid_p3, p->f3.threads, p->f3.smem_p3, st>>>(fp);
-        p->f3.p4<<<p->f3.grid_p2, p->f3.threads, p->f3.smem_p2, st>>>(fp);
-        p->f3.p5<<<p->f3.grid_p1, p->f3.threads, p->f3.smem_p1, st>>>(fp);
+        // P2..P5 as programmatic dependent launches (tsdr_fft3.cuh: pdl_wait); TSDR_FFT_PDL=0 launches them the ordinary way
+        const char* pe = getenv("TSDR_FFT_PDL");
+        const bool pdl = !(pe && pe[0] == '0');
+        auto launch = [&](void (*k)(FftParams), int grid, size_t smem) {
+            if (!pdl) { k<<<grid, p->f3.threads, smem, st>>>(fp); return; }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)p->f3.threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, k, fp);
+        };
+        launch(p->f3.p2, p->f3.grid_p2, p->f3.smem_p2);
+        launch(p->f3.p3, p->f3.grid_p3, p->f3.smem_p3);
+        launch(p->f3.p4, p->f3.grid_p2, p->f3.smem_p2);
+        launch(p->f3.p5, p->f3.grid_p1, p->f3.smem_p1);
         p->launches += 2;
     } else if (p->has_fast && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) {
         const int grid_cols = fp.B >> p->fast.logc;

@@ -25,6 +25,14 @@
 
 namespace tsdr {
 
+// Programmatic dependent launch between the five passes: every pass lets its successor start launching as soon as all
+// of its own CTAs are resident (launch_dependents at the top), and the successor blocks at pdl_wait() -- after it has
+// built its per-CTA twiddle tables, before its first read of T -- until this grid has completed and flushed.  The
+// successor's table prologue (a few hundred dependent look-ups, ~1.5 us) and its launch latency then overlap the
+// partially filled last wave of this pass.  Both instructions are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int LOGNA, int LOGNB, int LOGNC, int LOGC1, int LOGC2, int LOGR, int LOGTAB, int LOGNT>
 struct Fft3 {
     static constexpr int NA = 1 << LOGNA, NB = 1 << LOGNB, NC = 1 << LOGNC;
@@ -59,6 +67,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p1(FftParams p) {
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x << LOGC;
     const ColLayoutCt<LOGC> lay;
+    pdl_launch_dependents();
     load_twiddles<F::LOGNA_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
     for (int k = tid; k < NA; k += F::NT_v) tw_step[k] = twiddle_n(p, 2 * (int64_t)k);
     // W_M^(ka r) for the CTA's columns r = r0 + 2 j as the product of two small tables over ka = 16 kh + kl
@@ -117,6 +126,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
     __shared__ float2 tw_step[NB];   // forward: W_M'^kb, the step from column c to c + 1
                                      // inverse: conj W_M^(ka b NC), the row part of conj W_M^(ka r), r = b NC + c
     __shared__ float2 tw_col[HALF];  // inverse: conj W_M^(ka (c0 + 2 j)), its column part
+    pdl_launch_dependents();
     load_twiddles<F::LOGNB_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
     __shared__ float2 tw_kh[NB / 16][HALF];   // forward: W_M'^(kb c) for c = c0 + 2 j, kb = 16 kh + kl, as a product
     __shared__ float2 tw_kl[16][HALF];
@@ -135,6 +145,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p24(FftParams p) {
     const float2 step_inv = cconj(twiddle_n(p, 2 * (int64_t)ka));   // inverse: conj W_M^ka, the same for the whole CTA
     static_assert(F::NT_v % HALF == 0, "each thread keeps one column pair");
     const int c2 = (tid & (HALF - 1)) * 2;       // this thread's column pair in every loop below
+    pdl_wait();                                  // T is the previous pass's output
 #pragma unroll
     for (int i = tid / HALF; i < NB; i += F::NT_v / HALF) {   // forward: i = b ; inverse: i = kb
         const int pos = DIR > 0 ? i : digit_pos_ct<F::LOGNB_v>(i);
@@ -179,6 +190,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
     __shared__ float2 tw_rstep[2 * R]; // conj W_M'^kb of smem row srow: the step from column c to c + 1 in the write-back
     __shared__ float2 tw_hi[2 * R][NC / 16];   // conj W_M'^(kb 16 ch) and
     __shared__ float2 tw_lo[2 * R][8];         // conj W_M'^(kb cl), cl even: the write-back twiddle of column 16 ch + cl
+    pdl_launch_dependents();
     load_twiddles<LOGNC, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
     // slot s in [0, R): rows (rowA, rowB); smem row s holds rowA, smem row R + s holds rowB
     auto rowA_of = [&](int s) { return special ? t0 + s : NB + t0 + s; };
@@ -200,6 +212,7 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p3(FftParams p) {
         if (q < NC / 16) tw_hi[srow][q] = cconj(twiddle_n(p, (kb * 16 * q) << (LOGNA + 1)));
         else tw_lo[srow][q - NC / 16] = cconj(twiddle_n(p, (kb * 2 * (q - NC / 16)) << (LOGNA + 1)));
     }
+    pdl_wait();                                // T is the previous pass's output
     if (!special) {
         // The regular CTAs (all but a handful): every slot is valid and row A never equals row B, and because the
         // thread count is a multiple of the row length each thread keeps ONE column (pair) for the whole kernel --
@@ -307,9 +320,11 @@ __global__ void __launch_bounds__(F::NT_v, F::MINB_v) k3_p5(FftParams p) {
     const ColLayoutCt<LOGC> lay;
     const float4* T4 = reinterpret_cast<const float4*>(p.T);
     __shared__ float2 tw_s[NA];
+    pdl_launch_dependents();
     load_twiddles<F::LOGNA_v, F::LOGTAB_v, F::NT_v>(tw_s, p.twB, tid);
     static_assert(F::NT_v % HALF == 0, "each thread keeps one column pair");
     const int c2 = (tid & (HALF - 1)) * 2;
+    pdl_wait();                                  // T is the previous pass's output
 #pragma unroll
     for (int ka = tid / HALF; ka < NA; ka += F::NT_v / HALF) {
         *reinterpret_cast<float4*>(&sm[lay(c2, digit_pos_ct<F::LOGNA_v>(ka))]) = T4[(((int64_t)ka << F::LOGNBC_v) + r0 + c2) >> 1];
