@@ -17,7 +17,7 @@ def iq(n):
     return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
 
 
-which = set(sys.argv[1:]) or {"demod", "resample", "vsync", "chain", "autocorr", "spectrum", "upsampler"}
+which = set(sys.argv[1:]) or {"demod", "resample", "vsync", "chain", "fullres", "autocorr", "spectrum", "upsampler"}
 if "demod" in which:
     x = iq(10007)
     tsdr.amDemod(x); tsdr.invert_amDemod(x); tsdr.fmDemod(x); tsdr.abs2(x); tsdr.fullScale(np.abs(x)); tsdr.findmax(np.abs(x))
@@ -41,6 +41,17 @@ if "chain" in which:
             ch.push_i16(np.stack([z.real * 100, z.imag * 100], axis=1).astype(np.int16))
         ch.image(); ch.offsets(); ch.published()
         ch.close()
+if "fullres" in which:     # TSDR_CHAIN_FULLRES: k_render_full, k_project_p<true> (tiled TMA ring), k_beta<true>, k_accumulate_rows (bulk-copy ring)
+    for (Fs, mode, frames) in [(2e6, (400, 300, 60.0), 7), (2e6, (1053, 627, 60.0), 2)]:   # the second: rows that are not 16-byte multiples
+        cfg = tsdr.VideoMode(*mode)
+        S = tsdr.getImageDuration(cfg, Fs)
+        n = S * frames + 3
+        for pub in (False, True):
+            ch = tsdr.Chain(Fs, cfg, alpha=0.2, max_samples=n, publish_all=pub, full_res=True)
+            for k in range(2):
+                ch.push(iq(n))
+            ch.image(); ch.offsets(); ch.image_downgraded()
+            ch.close()
 if "autocorr" in which:
     for n in (1 << 12, 5000, 1 << 20):
         x = rng.random(n, dtype=np.float32) + 1
