@@ -210,7 +210,7 @@ int tsdr_comm_allreduce_f32(tsdr_comm* c, float* buf_dev, size_t n, float weight
     // out = sum over ranks of fl(weight_rank * in_rank): the block's EMA tail weight rides inside the collective.
     // EVERY rank takes the PreMulSum operator, also the one whose weight is 1 (the product is exact): NCCL picks its
     // algorithm per call from (size, type, operator), a built-in sum may go through NVLS on an NVSwitch box where a
-    // user-defined operator may not, and ranks that disagree on the algorithm never meet (8 ranks, 39.6 MB: a hang).
+    // user-defined operator may not, and ranks that disagree on the algorithm never meet.
     ncclRedOp_t op;
     TSDR_NCCL(api, api->RedOpCreatePreMulSum(&op, &weight, kNcclFloat32, kNcclScalarHostImmediate, c->comm));
     ncclResult_t r = api->AllReduce(buf_dev, buf_dev, n, kNcclFloat32, op, c->comm, st);
