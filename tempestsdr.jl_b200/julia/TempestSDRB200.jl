@@ -138,9 +138,9 @@ end
 
 # β_x / β_y of the Julia struct, copied out on demand (column-major, (1+wmax-wmin) x n)
 function betas(sync::SyncXY{Float32})
-    b = Ref{Cint}.((0, 0, 0, 0))
-    check(ccall((:tsdr_sync_bounds, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), sync.handle, b...))
-    wmin_y, wmax_y, wmin_x, wmax_x = getindex.(b)
+    b1 = Ref{Cint}(0); b2 = Ref{Cint}(0); b3 = Ref{Cint}(0); b4 = Ref{Cint}(0)   # ccall takes no splatted arguments
+    check(ccall((:tsdr_sync_bounds, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), sync.handle, b1, b2, b3, b4))
+    wmin_y, wmax_y, wmin_x, wmax_x = Int(b1[]), Int(b2[]), Int(b3[]), Int(b4[])
     βx = Matrix{Float32}(undef, 1 + wmax_x - wmin_x, sync.n_x); βy = Matrix{Float32}(undef, 1 + wmax_y - wmin_y, sync.n_y)
     GC.@preserve βx βy check(ccall((:tsdr_sync_get_beta, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
                                    sync.handle, pointer(βx), pointer(βy)))
