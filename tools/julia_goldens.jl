@@ -19,7 +19,7 @@ const HERE = normpath(joinpath(@__DIR__, ".."))
 const IN = joinpath(HERE, "tests", "golden", "julia_inputs")
 const OUT = length(ARGS) >= 2 ? ARGS[2] : joinpath(HERE, "tests", "golden", "julia_v1")
 
-module Ref
+module TSRef            # (not `Ref`: that would shadow Base.Ref in Main)
     # the reference's hot-path sources, as they lie in the checkout
     using Reexport
     const SRC = joinpath(Main.REF, "src")
@@ -31,8 +31,8 @@ module Ref
     include(joinpath(SRC, "FrameSynchronisation.jl"));  @reexport using .FrameSynchronisation
     include(joinpath(SRC, "GetSpectrum.jl"));           @reexport using .GetSpectrum
 end
-using .Ref
-import .Ref: amDemod, invert_amDemod, fmDemod, VideoMode, find_closest_configuration, allVideoConfigurations
+using .TSRef
+import .TSRef: amDemod, invert_amDemod, fmDemod, VideoMode, find_closest_configuration, allVideoConfigurations
 
 mkpath(OUT)
 const MANIFEST = String[]
