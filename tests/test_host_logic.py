@@ -63,3 +63,22 @@ def test_shard_helpers_cover_every_hypothesis_once():
         assert seen == list(range(n))
         blocks = [parallel.shard_contiguous(n, w, r) for r in range(w)]
         assert blocks[0][0] == 0 and blocks[-1][1] == n and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+
+
+def test_bench_workloads_follow_baseline_configs():
+    """bench.py's workload table is BASELINE.json's configs[1..4]: sample rates, total rasters,
+    buffer sizes; the headline default is the north-star configuration (cfg 3)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    w = bench.WORKLOADS
+    assert (w["cfg2"]["Fs"], w["cfg2"]["x_t"], w["cfg2"]["y_t"], w["cfg2"]["fv"]) == (20e6, 2576, 1125, 60.0)
+    assert (w["cfg3"]["Fs"], w["cfg3"]["x_t"], w["cfg3"]["y_t"], w["cfg3"]["fv"]) == (200e6, 2720, 1481, 60.0)
+    assert (w["cfg5"]["Fs"], w["cfg5"]["x_t"], w["cfg5"]["y_t"], w["cfg5"]["fv"], w["cfg5"]["total_frames"]) == (200e6, 4400, 2250, 30.0, 1000)
+    assert w["cfg4"]["n_ech"] == 1 << 26 and w["cfg3"]["n_ech"] == 10 ** 8
+    src = open(os.path.join(root, "bench.py")).read()
+    assert 'default="cfg3"' in src and '"cfg5_fullres"' in src          # headline workload; the full-resolution leg is selectable
+    assert "TSDR_BENCH_EXTRAS_DEADLINE" in src                          # the collective legs run under a watchdog
