@@ -905,8 +905,8 @@ def main():
             also = {}
             # The headline above is complete.  The extras below contain collectives (cfg 5); should one of them ever hang
             # (a rank lost, a collective mismatch) the run must still end with its line: after TSDR_BENCH_EXTRAS_DEADLINE
-            # seconds (default 420) every rank leaves, rank 0 printing the headline with whatever extras had finished.
-            deadline = float(os.environ.get("TSDR_BENCH_EXTRAS_DEADLINE", "420"))
+            # seconds (default 240) every rank leaves, rank 0 printing the headline with whatever extras had finished.
+            deadline = float(os.environ.get("TSDR_BENCH_EXTRAS_DEADLINE", "240"))
 
             def _give_up():
                 if rank == 0:
